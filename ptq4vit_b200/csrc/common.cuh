@@ -1,0 +1,87 @@
+// Shared device/host declarations for the PTQ4ViT scale-factor search on sm_100a.
+//
+// Data model:
+//   * "operand image": a quantised matrix [rows][K] stored tile-wise in the tcgen05
+//     no-swizzle K-major canonical layout so that one contiguous bulk copy (TMA 1-D,
+//     cp.async.bulk) lands a ready-to-multiply tile in shared memory:
+//         image[tile][chunk][128 rows][16 bytes]      (chunk = 16 bytes of K)
+//     K is cut into "segments" (intersection of the weight column blocks and the
+//     activation chunks, each padded to a multiple of 32 bytes) -- inside one
+//     segment both step sizes are constant, so the integer accumulation is exact.
+//   * "job": one <=128-byte-per-row slice of a segment = one shared-memory stage =
+//     up to 4 tcgen05.mma K-steps.  Consecutive jobs of a segment accumulate into
+//     one TMEM accumulator ("group"); the epilogue consumes one accumulator at a time.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#define P4V_TILE 128           // rows per operand tile == UMMA M == UMMA N
+#define P4V_JOB_KB 128         // max bytes of K per row and job
+#define P4V_MAX_JOBS 192
+#define P4V_MAX_GROUPS 96
+#define P4V_MAX_CAND 128
+#define P4V_CG 16              // columns per scale / score group
+#define P4V_TILE_CG (P4V_TILE / P4V_CG)   // 8
+
+enum : uint8_t {
+  P4V_JOB_FIRST  = 1,   // first job of an accumulator group
+  P4V_JOB_LAST   = 2,   // last job of an accumulator group
+  P4V_JOB_RCAND  = 4,   // row operand comes from the candidate plane
+  P4V_JOB_CCAND  = 8,   // column operand comes from the candidate plane
+};
+
+struct __align__(16) P4VJob {
+  uint32_t r_off;      // byte offset inside the row-operand tile image
+  uint32_t c_off;      // byte offset inside the column-operand tile image
+  uint16_t kb;         // bytes of K per row (multiple of 32, <= P4V_JOB_KB)
+  uint8_t  flags;
+  uint8_t  group;      // accumulator group index (row of the scale table)
+  uint32_t pad;
+};
+
+// score-group mapping of the 16-column groups (used by the sweep for scales and by
+// the reduction for the argmax groups)
+enum { P4V_SG_COLUMN = 0,   // scale group = global 16-column group index (Linear)
+       P4V_SG_PROBLEM = 1   // scale group = problem % nsg (head-wise MatMul)
+};
+
+struct SweepParams {
+  const uint8_t* R_cur;  const uint8_t* R_cand;
+  const uint8_t* C_cur;  const uint8_t* C_cand;
+  unsigned long long R_tile_bytes, C_tile_bytes;            // 128 * padded K bytes (current planes)
+  unsigned long long R_cand_tile_bytes, C_cand_tile_bytes;  // same for the candidate planes
+  unsigned long long R_cand_stride, C_cand_stride;          // bytes between candidate planes
+  int P, M, N, tiles_m, tiles_n;
+  const float* Y; const float* Gr; const float* bias;   // bias may be null
+  const float* gscale;                                  // device scalar: power-of-two gradient scale
+  long long ld, prob_stride;
+  const P4VJob* jobs;       // [n_fixed_jobs] then [n_cand_jobs]
+  int n_fixed_jobs, n_cand_jobs, n_fixed_groups, n_cand_groups;
+  const float* fix_scale;   // [n_fixed_groups][nsg]
+  const float* candA;       // [n_cand][nsg]
+  const float* candB;       // [n_cand_groups][nsg]
+  int nsg, sg_mode;
+  int n_cand;
+  float* partial;           // [tiles_total][n_cand][4][8]
+  float* out;               // if non-null: write bias + sum(scale*acc) of the fixed groups (quant_forward), no candidates
+  int order;                // 0: tile_m fastest, 1: tile_n fastest
+  int is_int8;
+};
+
+static inline __host__ __device__ int p4v_cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// ---- error plumbing (host) --------------------------------------------------
+#ifdef __cplusplus
+extern "C" void p4v_set_error(const char* fmt, ...);
+#endif
+#define P4V_CUDA_OK(expr)                                                            \
+  do { cudaError_t _e = (expr);                                                      \
+       if (_e != cudaSuccess) { p4v_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+                                return 2; } } while (0)
+#define P4V_REQUIRE(cond, ...)                                                       \
+  do { if (!(cond)) { p4v_set_error(__VA_ARGS__); return 1; } } while (0)
+
+// ---- kernel launchers shared between translation units ----------------------
+int p4v_launch_sweep_tc(const SweepParams& p, int num_sms, cudaStream_t st);
+int p4v_launch_sweep_simt(const SweepParams& p, cudaStream_t st);

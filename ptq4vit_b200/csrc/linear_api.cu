@@ -1,0 +1,468 @@
+// C-ABI for the Linear scale-factor search: host-side planning (segments, jobs,
+// workspace carving) + the per-step launch sequence.  See include/ptq4vit_b200.h.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/ptq4vit_b200.h"
+#include "prep.cuh"
+
+// ---------------------------------------------------------------- error / misc
+static thread_local char g_err[512] = "";
+static long long g_launches = 0;
+extern "C" __attribute__((visibility("default"))) void p4v_set_error(const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+}
+extern "C" const char* p4v_last_error(void) { return g_err; }
+extern "C" int p4v_version(void) { return 100; }
+extern "C" long long p4v_launch_count(void) { return g_launches; }
+void p4v_count_launch() { ++g_launches; }
+
+int p4v_num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+namespace {
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct BSeg { int k0, klen, h, a, kb; int woff, xoff_p, xoff_n, xcoff; };   // offsets: bytes in the padded row
+struct Step { int job_off, nfj, ncj, nfg, ncg, meta_fix, meta_cand, commit_off, ncommit, commit_chunks; };
+
+struct LinPlan {
+  p4v_linear_desc d;
+  bool i8, twin;
+  int ew, M, K, O, tiles_m, tiles_o, nsg, crb_rows, crb_cols, crb_acts, w_qmax, a_qmax;
+  float d_neg;
+  std::vector<BSeg> segs;
+  int KB_W, KB_X, KB_Xc;
+  std::vector<P4VJob> jobs; std::vector<GroupMeta> metas; std::vector<CommitSeg> commits;
+  std::vector<P4VSeg> segsW, segsX, segsXc;
+  std::vector<Step> wsteps, xsteps;
+  Step fwd;   // quant_forward: every segment is a fixed group
+  std::vector<float> factors;
+  int max_groups;
+  // workspace offsets
+  size_t o_factors, o_keys, o_dW0, o_dW, o_dX0, o_dX, o_gscale, o_scores, o_best, o_fix, o_candA, o_candB, o_jobs,
+      o_metas, o_segsW, o_segsX, o_segsXc, o_commits, o_partial, o_Wcur, o_Xcur, o_Wcand, o_Xcand, total;
+};
+
+void add_group(LinPlan& p, int r_off_bytes, int c_off_bytes, int kb, uint8_t src_flags, int group_idx, int& njobs) {
+  for (int b = 0; b < kb; b += P4V_JOB_KB) {
+    P4VJob j{};
+    const int len = std::min(P4V_JOB_KB, kb - b);
+    j.r_off = (uint32_t)(r_off_bytes + b) * P4V_TILE;
+    j.c_off = (uint32_t)(c_off_bytes + b) * P4V_TILE;
+    j.kb = (uint16_t)len;
+    j.flags = src_flags | (b == 0 ? P4V_JOB_FIRST : 0) | (b + len >= kb ? P4V_JOB_LAST : 0);
+    j.group = (uint8_t)group_idx;
+    p.jobs.push_back(j);
+    ++njobs;
+  }
+}
+
+int build_plan(const p4v_linear_desc* d, LinPlan& p, bool with_search) {
+  P4V_REQUIRE(d != nullptr, "null desc");
+  p.d = *d;
+  p.M = d->rows; p.K = d->in_features; p.O = d->out_features;
+  P4V_REQUIRE(p.M > 0 && p.K > 0 && p.O > 0, "linear: empty shape (rows=%d in=%d out=%d)", p.M, p.K, p.O);
+  P4V_REQUIRE(d->n_V >= 1 && d->n_H >= 1 && d->n_a >= 1, "linear: n_V/n_H/n_a must be >= 1");
+  P4V_REQUIRE(p.K % d->n_H == 0 && p.K % d->n_a == 0 && p.O % d->n_V == 0,
+              "linear: in_features must divide by n_H and n_a, out_features by n_V (reference views, linear.py:117-119)");
+  P4V_REQUIRE(d->tokens >= 1 && p.M % d->tokens == 0, "linear: rows must be a multiple of tokens");
+  P4V_REQUIRE(d->w_bit >= 2 && d->w_bit <= 8 && d->a_bit >= 2 && d->a_bit <= 8, "linear: bit widths must be in [2,8]");
+  P4V_REQUIRE(d->eq_n >= 1 && d->eq_n <= P4V_MAX_CAND, "linear: eq_n must be in [1,%d]", P4V_MAX_CAND);
+  p.crb_rows = p.O / d->n_V; p.crb_cols = p.K / d->n_H; p.crb_acts = p.K / d->n_a;
+  P4V_REQUIRE(d->n_V == 1 || p.crb_rows % P4V_CG == 0, "linear: out_features/n_V must be a multiple of 16 (got %d)", p.crb_rows);
+  p.w_qmax = 1 << (d->w_bit - 1); p.a_qmax = 1 << (d->a_bit - 1);
+  p.twin = d->post_gelu != 0;
+  p.d_neg = (float)(0.16997124254703522 / (double)p.a_qmax);
+  p.tiles_m = p4v_cdiv(p.M, P4V_TILE); p.tiles_o = p4v_cdiv(p.O, P4V_TILE);
+  p.nsg = p.tiles_o * P4V_TILE_CG;
+
+  // K segments = intersections of the weight column blocks and the activation chunks
+  std::vector<int> cuts;
+  for (int h = 0; h <= d->n_H; ++h) cuts.push_back(h * p.crb_cols);
+  for (int a = 0; a <= d->n_a; ++a) cuts.push_back(a * p.crb_acts);
+  std::sort(cuts.begin(), cuts.end());
+  cuts.erase(std::unique(cuts.begin(), cuts.end()), cuts.end());
+  int min_len = p.K;
+  for (size_t i = 0; i + 1 < cuts.size(); ++i) min_len = std::min(min_len, cuts[i + 1] - cuts[i]);
+  if (d->operand == P4V_OPERAND_INT8) p.i8 = true;
+  else if (d->operand == P4V_OPERAND_BF16) p.i8 = false;
+  else p.i8 = min_len >= 64;     // short slabs are epilogue bound: integer-valued bf16 saves the int->float converts
+  p.ew = p.i8 ? 1 : 2;
+  p.segs.clear();
+  int off = 0;
+  for (size_t i = 0; i + 1 < cuts.size(); ++i) {
+    BSeg s{};
+    s.k0 = cuts[i]; s.klen = cuts[i + 1] - cuts[i];
+    s.h = s.k0 / p.crb_cols; s.a = s.k0 / p.crb_acts;
+    s.kb = (int)align_up((size_t)s.klen * p.ew, 32);
+    s.woff = off; s.xoff_p = off; s.xcoff = off;
+    off += s.kb;
+    p.segs.push_back(s);
+  }
+  p.KB_W = off; p.KB_Xc = off;
+  p.KB_X = p.twin ? 2 * off : off;
+  for (auto& s : p.segs) s.xoff_n = p.twin ? off + s.xoff_p : -1;
+  P4V_REQUIRE((size_t)p.KB_X * P4V_TILE < (1ull << 32), "linear: in_features too large");
+
+  // quantisation segment tables
+  p.segsW.clear(); p.segsX.clear(); p.segsXc.clear();
+  for (auto& s : p.segs) {
+    P4VSeg w{s.k0, s.klen, s.woff * P4V_TILE, s.h, 0.f, (float)-p.w_qmax, (float)(p.w_qmax - 1)};
+    p.segsW.push_back(w);
+    P4VSeg x{s.k0, s.klen, s.xoff_p * P4V_TILE, s.a, 0.f, p.twin ? 0.f : (float)-p.a_qmax, (float)(p.a_qmax - 1)};
+    p.segsX.push_back(x);
+    P4VSeg xc = x; xc.dst_off = s.xcoff * P4V_TILE;
+    p.segsXc.push_back(xc);
+  }
+  if (p.twin)
+    for (auto& s : p.segs) {
+      P4VSeg n{s.k0, s.klen, s.xoff_n * P4V_TILE, s.a, p.d_neg, (float)-p.a_qmax, 0.f};
+      p.segsX.push_back(n);
+    }
+
+  // candidate factors (python floats -> fp32, linear.py:544-545)
+  p.factors.resize(d->eq_n + 1);
+  for (int i = 0; i <= d->eq_n; ++i) p.factors[i] = (float)(d->eq_alpha + i * (d->eq_beta - d->eq_alpha) / d->eq_n);
+
+  // steps
+  p.jobs.clear(); p.metas.clear(); p.commits.clear(); p.wsteps.clear(); p.xsteps.clear();
+  p.max_groups = 1;
+  auto begin_step = [&](Step& st) { st = Step{}; st.job_off = (int)p.jobs.size(); st.commit_off = (int)p.commits.size(); };
+  auto fixed_group = [&](Step& st, const BSeg& s, bool neg) {
+    add_group(p, neg ? s.xoff_n : s.xoff_p, s.woff, s.kb, 0, st.nfg, st.nfj);
+    p.metas.push_back(GroupMeta{(short)s.h, (short)s.a, (short)(neg ? 1 : 0), 0});
+    ++st.nfg;
+  };
+  if (with_search) {
+    for (int h = 0; h < d->n_H; ++h) {
+      Step st; begin_step(st);
+      st.meta_fix = (int)p.metas.size();
+      for (auto& s : p.segs) if (s.h != h) { fixed_group(st, s, false); if (p.twin) fixed_group(st, s, true); }
+      st.meta_cand = (int)p.metas.size();
+      for (auto& s : p.segs) if (s.h == h) {
+        add_group(p, s.xoff_p, s.woff, s.kb, P4V_JOB_CCAND, st.ncg, st.ncj);
+        p.metas.push_back(GroupMeta{(short)s.h, (short)s.a, 0, 0}); ++st.ncg;
+        if (p.twin) {
+          add_group(p, s.xoff_n, s.woff, s.kb, P4V_JOB_CCAND, st.ncg, st.ncj);
+          p.metas.push_back(GroupMeta{(short)s.h, (short)s.a, 1, 0}); ++st.ncg;
+        }
+        p.commits.push_back(CommitSeg{s.woff * P4V_TILE, s.woff * P4V_TILE, s.kb});
+        st.commit_chunks += s.kb / 16; ++st.ncommit;
+      }
+      p.wsteps.push_back(st);
+    }
+    for (int a = 0; a < d->n_a; ++a) {
+      Step st; begin_step(st);
+      st.meta_fix = (int)p.metas.size();
+      for (auto& s : p.segs) { if (s.a != a) fixed_group(st, s, false); if (p.twin) fixed_group(st, s, true); }
+      st.meta_cand = (int)p.metas.size();
+      for (auto& s : p.segs) if (s.a == a) {
+        add_group(p, s.xcoff, s.woff, s.kb, P4V_JOB_RCAND, st.ncg, st.ncj);
+        p.metas.push_back(GroupMeta{(short)s.h, (short)s.a, 0, 0}); ++st.ncg;
+        p.commits.push_back(CommitSeg{s.xcoff * P4V_TILE, s.xoff_p * P4V_TILE, s.kb});
+        st.commit_chunks += s.kb / 16; ++st.ncommit;
+      }
+      p.xsteps.push_back(st);
+    }
+  }
+  {
+    Step st; begin_step(st);
+    st.meta_fix = (int)p.metas.size();
+    for (auto& s : p.segs) { fixed_group(st, s, false); if (p.twin) fixed_group(st, s, true); }
+    st.meta_cand = (int)p.metas.size();
+    p.fwd = st;
+  }
+  auto check = [&](const Step& st) {
+    return st.nfj + st.ncj <= P4V_MAX_JOBS && st.nfg <= P4V_MAX_GROUPS && st.ncg <= P4V_MAX_GROUPS;
+  };
+  for (auto& st : p.wsteps) { P4V_REQUIRE(check(st), "linear: too many K segments for one step (n_H/n_a/in_features)"); p.max_groups = std::max(p.max_groups, std::max(st.nfg, st.ncg)); }
+  for (auto& st : p.xsteps) { P4V_REQUIRE(check(st), "linear: too many K segments for one step (n_H/n_a/in_features)"); p.max_groups = std::max(p.max_groups, std::max(st.nfg, st.ncg)); }
+  P4V_REQUIRE(check(p.fwd), "linear: too many K segments for quant_forward");
+  p.max_groups = std::max(p.max_groups, p.fwd.nfg);
+
+  // workspace carving
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o = align_up(o + bytes, 256); return r; };
+  const int n_c = d->eq_n;
+  p.o_factors = take((n_c + 1) * 4);
+  p.o_keys = take((d->n_V * d->n_H + d->n_a + 1) * 4);
+  p.o_dW0 = take(d->n_V * d->n_H * 4); p.o_dW = take(d->n_V * d->n_H * 4);
+  p.o_dX0 = take(d->n_a * 4); p.o_dX = take(d->n_a * 4);
+  p.o_gscale = take(4);
+  p.o_scores = take((size_t)n_c * std::max(d->n_V, 1) * 8);
+  p.o_best = take(std::max(d->n_V, 1) * 4);
+  p.o_fix = take((size_t)p.max_groups * p.nsg * 4);
+  p.o_candA = take((size_t)n_c * p.nsg * 4);
+  p.o_candB = take((size_t)p.max_groups * p.nsg * 4);
+  p.o_jobs = take(p.jobs.size() * sizeof(P4VJob));
+  p.o_metas = take(p.metas.size() * sizeof(GroupMeta));
+  p.o_segsW = take(p.segsW.size() * sizeof(P4VSeg));
+  p.o_segsX = take(p.segsX.size() * sizeof(P4VSeg));
+  p.o_segsXc = take(p.segsXc.size() * sizeof(P4VSeg));
+  p.o_commits = take(std::max<size_t>(1, p.commits.size()) * sizeof(CommitSeg));
+  p.o_partial = take(with_search ? (size_t)p.tiles_m * p.tiles_o * n_c * 32 * 4 : 4);
+  p.o_Wcur = take((size_t)p.tiles_o * P4V_TILE * p.KB_W);
+  p.o_Xcur = take((size_t)p.tiles_m * P4V_TILE * p.KB_X);
+  p.o_Wcand = take(with_search ? (size_t)n_c * p.tiles_o * P4V_TILE * p.KB_W : 4);
+  p.o_Xcand = take(with_search ? (size_t)n_c * p.tiles_m * P4V_TILE * p.KB_Xc : 4);
+  p.total = o;
+  return 0;
+}
+
+template <class T> T* at(void* ws, size_t off) { return reinterpret_cast<T*>(static_cast<uint8_t*>(ws) + off); }
+
+int upload_tables(const LinPlan& p, void* ws, cudaStream_t st) {
+  P4V_CUDA_OK(cudaMemcpyAsync(at<void>(ws, p.o_factors), p.factors.data(), p.factors.size() * 4, cudaMemcpyHostToDevice, st));
+  P4V_CUDA_OK(cudaMemcpyAsync(at<void>(ws, p.o_jobs), p.jobs.data(), p.jobs.size() * sizeof(P4VJob), cudaMemcpyHostToDevice, st));
+  P4V_CUDA_OK(cudaMemcpyAsync(at<void>(ws, p.o_metas), p.metas.data(), p.metas.size() * sizeof(GroupMeta), cudaMemcpyHostToDevice, st));
+  P4V_CUDA_OK(cudaMemcpyAsync(at<void>(ws, p.o_segsW), p.segsW.data(), p.segsW.size() * sizeof(P4VSeg), cudaMemcpyHostToDevice, st));
+  P4V_CUDA_OK(cudaMemcpyAsync(at<void>(ws, p.o_segsX), p.segsX.data(), p.segsX.size() * sizeof(P4VSeg), cudaMemcpyHostToDevice, st));
+  P4V_CUDA_OK(cudaMemcpyAsync(at<void>(ws, p.o_segsXc), p.segsXc.data(), p.segsXc.size() * sizeof(P4VSeg), cudaMemcpyHostToDevice, st));
+  if (!p.commits.empty())
+    P4V_CUDA_OK(cudaMemcpyAsync(at<void>(ws, p.o_commits), p.commits.data(), p.commits.size() * sizeof(CommitSeg), cudaMemcpyHostToDevice, st));
+  return 0;
+}
+
+int quant_W(const LinPlan& p, void* ws, const float* W, const float* delta, bool cand, cudaStream_t st) {
+  QuantImageArgs q{};
+  q.src = W; q.ld = p.K; q.prob_stride = 0; q.src_transposed = 0;
+  q.P = 1; q.rows = p.O; q.tiles = p.tiles_o;
+  q.dst = at<uint8_t>(ws, cand ? p.o_Wcand : p.o_Wcur);
+  q.tile_bytes = (unsigned long long)P4V_TILE * p.KB_W; q.plane_stride = q.tile_bytes * p.tiles_o;
+  q.n_planes = cand ? p.d.eq_n : 1;
+  q.factors = cand ? at<float>(ws, p.o_factors) : nullptr;
+  q.delta = delta; q.rows_per_block = p.crb_rows; q.d_stride = p.d.n_H; q.d_mod = 1;
+  q.segs = at<P4VSeg>(ws, p.o_segsW); q.nseg = (int)p.segsW.size(); q.is_int8 = p.i8;
+  return p4v_quant_image(q, st);
+}
+
+int quant_X(const LinPlan& p, void* ws, const float* x, const float* delta, bool cand, cudaStream_t st) {
+  QuantImageArgs q{};
+  q.src = x; q.ld = p.K; q.prob_stride = 0; q.src_transposed = 0;
+  q.P = 1; q.rows = p.M; q.tiles = p.tiles_m;
+  q.dst = at<uint8_t>(ws, cand ? p.o_Xcand : p.o_Xcur);
+  q.tile_bytes = (unsigned long long)P4V_TILE * (cand ? p.KB_Xc : p.KB_X); q.plane_stride = q.tile_bytes * p.tiles_m;
+  q.n_planes = cand ? p.d.eq_n : 1;
+  q.factors = cand ? at<float>(ws, p.o_factors) : nullptr;
+  q.delta = delta; q.rows_per_block = p.M + P4V_TILE; q.d_stride = 0; q.d_mod = 1;   // single row block
+  q.segs = at<P4VSeg>(ws, cand ? p.o_segsXc : p.o_segsX); q.nseg = (int)(cand ? p.segsXc.size() : p.segsX.size());
+  q.is_int8 = p.i8;
+  return p4v_quant_image(q, st);
+}
+
+void fill_sweep(const LinPlan& p, void* ws, const Step& s, SweepParams& sp) {
+  sp = SweepParams{};
+  sp.R_cur = at<uint8_t>(ws, p.o_Xcur); sp.R_cand = at<uint8_t>(ws, p.o_Xcand);
+  sp.C_cur = at<uint8_t>(ws, p.o_Wcur); sp.C_cand = at<uint8_t>(ws, p.o_Wcand);
+  sp.R_tile_bytes = (unsigned long long)P4V_TILE * p.KB_X; sp.C_tile_bytes = (unsigned long long)P4V_TILE * p.KB_W;
+  sp.R_cand_tile_bytes = (unsigned long long)P4V_TILE * p.KB_Xc; sp.C_cand_tile_bytes = sp.C_tile_bytes;
+  sp.R_cand_stride = sp.R_cand_tile_bytes * p.tiles_m; sp.C_cand_stride = sp.C_cand_tile_bytes * p.tiles_o;
+  sp.P = 1; sp.M = p.M; sp.N = p.O; sp.tiles_m = p.tiles_m; sp.tiles_n = p.tiles_o;
+  sp.ld = p.O; sp.prob_stride = 0;
+  sp.gscale = at<float>(ws, p.o_gscale);
+  sp.jobs = at<P4VJob>(ws, p.o_jobs) + s.job_off;
+  sp.n_fixed_jobs = s.nfj; sp.n_cand_jobs = s.ncj; sp.n_fixed_groups = s.nfg; sp.n_cand_groups = s.ncg;
+  sp.fix_scale = at<float>(ws, p.o_fix); sp.candA = at<float>(ws, p.o_candA); sp.candB = at<float>(ws, p.o_candB);
+  sp.nsg = p.nsg; sp.sg_mode = P4V_SG_COLUMN;
+  sp.n_cand = p.d.eq_n;
+  sp.partial = at<float>(ws, p.o_partial);
+  sp.is_int8 = p.i8;
+}
+
+int run_sweep(const LinPlan& p, const SweepParams& sp, cudaStream_t st) {
+  p4v_count_launch();
+  if (p.d.kernel == P4V_KERNEL_SIMT) return p4v_launch_sweep_simt(sp, st);
+  return p4v_launch_sweep_tc(sp, p4v_num_sms(), st);
+}
+
+int tables_for(const LinPlan& p, void* ws, const Step& s, int kind, int target, cudaStream_t st) {
+  StepTablesArgs t{};
+  t.kind = kind; t.target = target;
+  t.dW = at<float>(ws, p.o_dW); t.dW0 = at<float>(ws, p.o_dW0); t.n_V = p.d.n_V; t.n_H = p.d.n_H; t.crb_rows = p.crb_rows;
+  t.dX = at<float>(ws, p.o_dX); t.dX0 = at<float>(ws, p.o_dX0); t.n_a = p.d.n_a; t.d_neg = p.d_neg;
+  t.factors = at<float>(ws, p.o_factors); t.n_cand = kind < 0 ? 0 : p.d.eq_n;
+  t.fixed_meta = at<GroupMeta>(ws, p.o_metas) + s.meta_fix; t.n_fixed_groups = s.nfg;
+  t.cand_meta = at<GroupMeta>(ws, p.o_metas) + s.meta_cand; t.n_cand_groups = s.ncg;
+  t.nsg = p.nsg;
+  t.fix_scale = at<float>(ws, p.o_fix); t.candA = at<float>(ws, p.o_candA); t.candB = at<float>(ws, p.o_candB);
+  if (kind < 0) t.kind = 0;
+  return p4v_step_tables(t, st);
+}
+
+int search_step(const LinPlan& p, void* ws, bool is_w, int idx, const float* bias, const float* y, const float* g,
+                float* score_log, cudaStream_t st) {
+  const Step& s = is_w ? p.wsteps[idx] : p.xsteps[idx];
+  int rc;
+  if ((rc = tables_for(p, ws, s, is_w ? 0 : 1, idx, st))) return rc;
+  SweepParams sp; fill_sweep(p, ws, s, sp);
+  sp.Y = y; sp.Gr = g; sp.bias = p.d.has_bias ? bias : nullptr;
+  sp.order = is_w ? 0 : 1;
+  if ((rc = run_sweep(p, sp, st))) return rc;
+  const int n_groups = is_w ? p.d.n_V : 1;
+  ReduceArgs r{};
+  r.partial = sp.partial; r.n_cand = p.d.eq_n; r.P = 1; r.tiles_m = p.tiles_m; r.tiles_n = p.tiles_o; r.order = sp.order;
+  r.mode = P4V_SG_COLUMN; r.n_groups = n_groups; r.cg_per_group = is_w ? p.crb_rows / P4V_CG : p.nsg;
+  r.inv_count = 1.0 / ((double)p.d.tokens * (double)(is_w ? p.crb_rows : p.O));
+  r.gscale = at<float>(ws, p.o_gscale); r.scores = at<double>(ws, p.o_scores);
+  if ((rc = p4v_reduce_scores(r, st))) return rc;
+  FinishArgs f{};
+  f.scores = r.scores; f.n_cand = p.d.eq_n; f.n_groups = n_groups; f.factors = at<float>(ws, p.o_factors);
+  if (is_w) { f.d0 = at<float>(ws, p.o_dW0); f.d = at<float>(ws, p.o_dW); f.d_stride = p.d.n_H; f.d_col = idx; }
+  else      { f.d0 = at<float>(ws, p.o_dX0); f.d = at<float>(ws, p.o_dX); f.d_stride = 0; f.d_col = idx; }
+  f.best = at<int>(ws, p.o_best); f.score_log = score_log;
+  f.cand = at<uint8_t>(ws, is_w ? p.o_Wcand : p.o_Xcand);
+  f.cand_tile_bytes = (unsigned long long)P4V_TILE * (is_w ? p.KB_W : p.KB_Xc);
+  f.cand_plane_stride = f.cand_tile_bytes * (is_w ? p.tiles_o : p.tiles_m);
+  f.cur = at<uint8_t>(ws, is_w ? p.o_Wcur : p.o_Xcur);
+  f.cur_tile_bytes = (unsigned long long)P4V_TILE * (is_w ? p.KB_W : p.KB_X);
+  f.P = 1; f.rows = is_w ? p.O : p.M; f.tiles = is_w ? p.tiles_o : p.tiles_m;
+  f.rows_per_group = is_w ? p.crb_rows : 0; f.problem_groups = 0;
+  f.segs = at<CommitSeg>(ws, p.o_commits) + s.commit_off; f.nseg = s.ncommit; f.commit_chunks = s.commit_chunks;
+  return p4v_finish_step(f, st);
+}
+
+int begin_impl(const LinPlan& p, const float* x, const float* W, const float* g, void* ws, cudaStream_t st) {
+  int rc;
+  if ((rc = upload_tables(p, ws, st))) return rc;
+  int* keys = at<int>(ws, p.o_keys);
+  const int nW = p.d.n_V * p.d.n_H;
+  if ((rc = p4v_keys_reset(keys, nW + p.d.n_a + 1, st))) return rc;
+  if ((rc = p4v_block_max(W, p.K, p.O, p.crb_rows, p.d.n_V, p.crb_cols, p.d.n_H, 1, keys, st))) return rc;
+  if ((rc = p4v_block_max(x, p.K, p.M, p.M, 1, p.crb_acts, p.d.n_a, p.twin ? 0 : 1, keys + nW, st))) return rc;
+  if ((rc = p4v_block_max(g, p.O, p.M, p.M, 1, p.O, 1, 1, keys + nW + p.d.n_a, st))) return rc;
+  if ((rc = p4v_keys_to_delta(keys, nW, (float)p.w_qmax - 0.5f, at<float>(ws, p.o_dW0), at<float>(ws, p.o_dW), st))) return rc;
+  if ((rc = p4v_keys_to_delta(keys + nW, p.d.n_a, (float)p.a_qmax - 0.5f, at<float>(ws, p.o_dX0), at<float>(ws, p.o_dX), st))) return rc;
+  if ((rc = p4v_make_gscale(keys + nW + p.d.n_a, at<float>(ws, p.o_gscale), st))) return rc;
+  if ((rc = quant_W(p, ws, W, at<float>(ws, p.o_dW0), false, st))) return rc;
+  if ((rc = quant_W(p, ws, W, at<float>(ws, p.o_dW0), true, st))) return rc;
+  if ((rc = quant_X(p, ws, x, at<float>(ws, p.o_dX0), false, st))) return rc;
+  if ((rc = quant_X(p, ws, x, at<float>(ws, p.o_dX0), true, st))) return rc;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int p4v_linear_workspace_bytes(const p4v_linear_desc* d, size_t* bytes) {
+  LinPlan p; int rc = build_plan(d, p, true);
+  if (rc) return rc;
+  P4V_REQUIRE(bytes != nullptr, "null output");
+  *bytes = p.total;
+  return 0;
+}
+
+extern "C" int p4v_linear_score_log_floats(const p4v_linear_desc* d, size_t* n) {
+  P4V_REQUIRE(d && n, "null argument");
+  *n = (size_t)d->search_round * ((size_t)d->n_H * d->eq_n * d->n_V + (size_t)d->n_a * d->eq_n);
+  return 0;
+}
+
+extern "C" int p4v_linear_begin(const p4v_linear_desc* d, const float* x, const float* weight, const float* bias,
+                                const float* raw_out, const float* raw_grad, void* workspace, size_t workspace_bytes, void* stream) {
+  (void)bias; (void)raw_out;
+  LinPlan p; int rc = build_plan(d, p, true);
+  if (rc) return rc;
+  P4V_REQUIRE(x && weight && raw_grad && workspace, "linear_begin: null pointer");
+  P4V_REQUIRE(workspace_bytes >= p.total, "linear_begin: workspace too small (%zu < %zu)", workspace_bytes, p.total);
+  return begin_impl(p, x, weight, raw_grad, workspace, (cudaStream_t)stream);
+}
+
+extern "C" int p4v_linear_search_w(const p4v_linear_desc* d, const float* bias, const float* raw_out, const float* raw_grad,
+                                   void* workspace, int32_t h_begin, int32_t h_end, float* score_log, void* stream) {
+  LinPlan p; int rc = build_plan(d, p, true);
+  if (rc) return rc;
+  P4V_REQUIRE(raw_out && raw_grad && workspace, "linear_search_w: null pointer");
+  P4V_REQUIRE(0 <= h_begin && h_begin <= h_end && h_end <= d->n_H, "linear_search_w: bad block range");
+  for (int h = h_begin; h < h_end; ++h) {
+    if ((rc = search_step(p, workspace, true, h, bias, raw_out, raw_grad, score_log, (cudaStream_t)stream))) return rc;
+    if (score_log) score_log += (size_t)d->eq_n * d->n_V;
+  }
+  return 0;
+}
+
+extern "C" int p4v_linear_search_a(const p4v_linear_desc* d, const float* bias, const float* raw_out, const float* raw_grad,
+                                   void* workspace, int32_t a_begin, int32_t a_end, float* score_log, void* stream) {
+  LinPlan p; int rc = build_plan(d, p, true);
+  if (rc) return rc;
+  P4V_REQUIRE(raw_out && raw_grad && workspace, "linear_search_a: null pointer");
+  P4V_REQUIRE(0 <= a_begin && a_begin <= a_end && a_end <= d->n_a, "linear_search_a: bad chunk range");
+  for (int a = a_begin; a < a_end; ++a) {
+    if ((rc = search_step(p, workspace, false, a, bias, raw_out, raw_grad, score_log, (cudaStream_t)stream))) return rc;
+    if (score_log) score_log += d->eq_n;
+  }
+  return 0;
+}
+
+extern "C" int p4v_linear_intervals(const p4v_linear_desc* d, void* workspace, float* w_interval, float* a_interval, void* stream) {
+  LinPlan p; int rc = build_plan(d, p, true);
+  if (rc) return rc;
+  P4V_REQUIRE(workspace && w_interval && a_interval, "linear_intervals: null pointer");
+  P4V_CUDA_OK(cudaMemcpyAsync(w_interval, at<float>(workspace, p.o_dW), (size_t)d->n_V * d->n_H * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  P4V_CUDA_OK(cudaMemcpyAsync(a_interval, at<float>(workspace, p.o_dX), (size_t)d->n_a * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
+
+extern "C" int p4v_linear_calibrate(const p4v_linear_desc* d, const float* x, const float* weight, const float* bias,
+                                    const float* raw_out, const float* raw_grad, void* workspace, size_t workspace_bytes,
+                                    float* w_interval, float* a_interval, float* score_log, void* stream) {
+  LinPlan p; int rc = build_plan(d, p, true);
+  if (rc) return rc;
+  P4V_REQUIRE(x && weight && raw_out && raw_grad && workspace && w_interval && a_interval, "linear_calibrate: null pointer");
+  P4V_REQUIRE(!d->has_bias || bias, "linear_calibrate: has_bias set but bias is null");
+  P4V_REQUIRE(workspace_bytes >= p.total, "linear_calibrate: workspace too small (%zu < %zu)", workspace_bytes, p.total);
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = begin_impl(p, x, weight, raw_grad, workspace, st))) return rc;
+  for (int e = 0; e < d->search_round; ++e) {
+    for (int h = 0; h < d->n_H; ++h) {
+      if ((rc = search_step(p, workspace, true, h, bias, raw_out, raw_grad, score_log, st))) return rc;
+      if (score_log) score_log += (size_t)d->eq_n * d->n_V;
+    }
+    for (int a = 0; a < d->n_a; ++a) {
+      if ((rc = search_step(p, workspace, false, a, bias, raw_out, raw_grad, score_log, st))) return rc;
+      if (score_log) score_log += d->eq_n;
+    }
+  }
+  P4V_CUDA_OK(cudaMemcpyAsync(w_interval, at<float>(workspace, p.o_dW), (size_t)d->n_V * d->n_H * 4, cudaMemcpyDeviceToDevice, st));
+  P4V_CUDA_OK(cudaMemcpyAsync(a_interval, at<float>(workspace, p.o_dX), (size_t)d->n_a * 4, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+extern "C" int p4v_linear_quant_forward_workspace_bytes(const p4v_linear_desc* d, size_t* bytes) {
+  LinPlan p; int rc = build_plan(d, p, false);
+  if (rc) return rc;
+  P4V_REQUIRE(bytes != nullptr, "null output");
+  *bytes = p.total;
+  return 0;
+}
+
+extern "C" int p4v_linear_quant_forward(const p4v_linear_desc* d, const float* x, const float* weight, const float* bias,
+                                        const float* w_interval, const float* a_interval, void* workspace,
+                                        size_t workspace_bytes, float* out, void* stream) {
+  LinPlan p; int rc = build_plan(d, p, false);
+  if (rc) return rc;
+  P4V_REQUIRE(x && weight && w_interval && a_interval && workspace && out, "linear_quant_forward: null pointer");
+  P4V_REQUIRE(workspace_bytes >= p.total, "linear_quant_forward: workspace too small (%zu < %zu)", workspace_bytes, p.total);
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = upload_tables(p, workspace, st))) return rc;
+  P4V_CUDA_OK(cudaMemcpyAsync(at<float>(workspace, p.o_dW), w_interval, (size_t)d->n_V * d->n_H * 4, cudaMemcpyDeviceToDevice, st));
+  P4V_CUDA_OK(cudaMemcpyAsync(at<float>(workspace, p.o_dX), a_interval, (size_t)d->n_a * 4, cudaMemcpyDeviceToDevice, st));
+  if ((rc = quant_W(p, workspace, weight, at<float>(workspace, p.o_dW), false, st))) return rc;
+  if ((rc = quant_X(p, workspace, x, at<float>(workspace, p.o_dX), false, st))) return rc;
+  if ((rc = tables_for(p, workspace, p.fwd, -1, 0, st))) return rc;
+  SweepParams sp; fill_sweep(p, workspace, p.fwd, sp);
+  sp.bias = d->has_bias ? bias : nullptr;
+  sp.out = out; sp.n_cand = 1; sp.order = 0;
+  sp.R_cand = nullptr; sp.C_cand = nullptr;
+  return run_sweep(p, sp, st);
+}

@@ -1,0 +1,82 @@
+// Support kernels around the sweep: min-max initialisation, operand-image
+// quantisation, per-step scale tables, deterministic score reduction, argmax +
+// commit of the chosen candidate.  All HBM-bound streaming work.
+#pragma once
+#include "common.cuh"
+
+struct P4VSeg {          // one K segment of an operand image
+  int k0, klen;          // source column range
+  int dst_off;           // byte offset of the segment inside the tile image ( = 128 * byte offset in the padded row )
+  int didx;              // column index into the step-size table (block / chunk id)
+  float fixed_delta;     // > 0: use this constant step size (twin-uniform negative part)
+  float lo, hi;          // clamp range
+};
+
+struct QuantImageArgs {
+  const float* src; long long ld; long long prob_stride;   // [P][rows][K], transposed read if src_kmajor == 0
+  int src_transposed;    // 1: element (row, k) lives at src[k * ld + row]  (MatMul B operand)
+  int P, rows, tiles;    // tiles per problem
+  uint8_t* dst; unsigned long long tile_bytes, plane_stride;
+  int n_planes;          // candidate planes (1 for the current image)
+  const float* factors;  // [n_planes] candidate factors or null (=> 1.0, no extra rounding)
+  const float* delta;    // step-size table: delta[rb * d_stride + seg.didx]
+  int rows_per_block;    // rb = (row / rows_per_block) (Linear W: crb_rows); 0 => rb = problem % d_mod
+  int d_stride, d_mod;
+  const P4VSeg* segs; int nseg;
+  int is_int8;
+};
+int p4v_quant_image(const QuantImageArgs& a, cudaStream_t st);
+
+// max / absmax of blocks of a row-major matrix, written as order-preserving int keys
+int p4v_block_max(const float* src, long long ld, int rows, int row_block, int n_row_blocks,
+                  int col_block, int n_col_blocks, int use_abs, int* keys, cudaStream_t st);
+// per-problem-group absmax of a [P][rows][cols] tensor: group = p % n_groups
+int p4v_group_absmax(const float* src, long long prob_elems, int P, int n_groups, int* keys, cudaStream_t st);
+int p4v_keys_reset(int* keys, int n, cudaStream_t st);
+// delta[i] = key_to_float(keys[i]) / denom ; optionally copy to a second array
+int p4v_keys_to_delta(const int* keys, int n, float denom, float* d0, float* d1, cudaStream_t st);
+// gscale = 2^-floor(log2(max|g|)) (1 if max is 0 / non-finite)
+int p4v_make_gscale(const int* key, float* gscale, cudaStream_t st);
+
+struct GroupMeta { short h, a; short neg; short pad; };   // neg: use the constant negative-part step size
+
+struct StepTablesArgs {
+  int kind;                  // 0: Linear W step, 1: Linear X step, 2: MatMul A step, 3: MatMul B step
+  int target;                // h (W step) / a (X step)
+  const float* dW; const float* dW0; int n_V, n_H, crb_rows;
+  const float* dX; const float* dX0; int n_a; float d_neg;
+  const float* factors; int n_cand;
+  const GroupMeta* fixed_meta; int n_fixed_groups;
+  const GroupMeta* cand_meta;  int n_cand_groups;
+  int nsg;
+  float* fix_scale; float* candA; float* candB;
+};
+int p4v_step_tables(const StepTablesArgs& a, cudaStream_t st);
+
+struct ReduceArgs {
+  const float* partial; int n_cand;
+  int P, tiles_m, tiles_n, order;
+  int mode;                  // P4V_SG_COLUMN: group = global16colgroup / cg_per_group ; P4V_SG_PROBLEM: group = p % n_groups
+  int n_groups, cg_per_group;
+  double inv_count;          // 1 / (tokens * features) normalisation of the reference's means
+  const float* gscale;
+  double* scores;            // [n_cand][n_groups]
+};
+int p4v_reduce_scores(const ReduceArgs& a, cudaStream_t st);
+
+struct CommitSeg { int src_off, dst_off, kb; };
+struct FinishArgs {
+  const double* scores; int n_cand, n_groups;
+  const float* factors;
+  const float* d0; float* d; int d_stride, d_col;    // d[g * d_stride + d_col] = fl(f[best_g] * d0[...])
+  int* best;                                         // [n_groups] (optional)
+  float* score_log;                                  // [n_cand][n_groups] fp32 (optional)
+  // image commit: rows of group g = [g*rows_per_group, (g+1)*rows_per_group) ; rows_per_group==0 -> all rows group 0
+  // ; problem mode: group = p % n_groups
+  const uint8_t* cand; unsigned long long cand_plane_stride, cand_tile_bytes;
+  uint8_t* cur; unsigned long long cur_tile_bytes;
+  int P, rows, tiles, rows_per_group, problem_groups;
+  const CommitSeg* segs; int nseg;
+  int commit_chunks;                                 // sum over segs of kb/16
+};
+int p4v_finish_step(const FinishArgs& a, cudaStream_t st);
