@@ -62,6 +62,7 @@ struct SweepParams {
   const float* candA;       // [n_cand][nsg]
   const float* candB;       // [n_cand_groups][nsg]
   int nsg, sg_mode;
+  unsigned long long cand_noA_mask;   // bit g set: candidate group g ignores candA (scale = candB only)
   int n_cand;
   float* partial;           // [tiles_total][n_cand][4][8]
   float* out;               // if non-null: write bias + sum(scale*acc) of the fixed groups (quant_forward), no candidates

@@ -119,16 +119,16 @@ int build_plan(const p4v_linear_desc* d, LinPlan& p, bool with_search) {
   // quantisation segment tables
   p.segsW.clear(); p.segsX.clear(); p.segsXc.clear();
   for (auto& s : p.segs) {
-    P4VSeg w{s.k0, s.klen, s.woff * P4V_TILE, s.h, 0.f, (float)-p.w_qmax, (float)(p.w_qmax - 1)};
+    P4VSeg w{s.k0, s.klen, s.woff * P4V_TILE, s.h, 0.f, (float)-p.w_qmax, (float)(p.w_qmax - 1), 0, 0.f, 0};
     p.segsW.push_back(w);
-    P4VSeg x{s.k0, s.klen, s.xoff_p * P4V_TILE, s.a, 0.f, p.twin ? 0.f : (float)-p.a_qmax, (float)(p.a_qmax - 1)};
+    P4VSeg x{s.k0, s.klen, s.xoff_p * P4V_TILE, s.a, 0.f, p.twin ? 0.f : (float)-p.a_qmax, (float)(p.a_qmax - 1), 0, 0.f, 0};
     p.segsX.push_back(x);
     P4VSeg xc = x; xc.dst_off = s.xcoff * P4V_TILE;
     p.segsXc.push_back(xc);
   }
   if (p.twin)
     for (auto& s : p.segs) {
-      P4VSeg n{s.k0, s.klen, s.xoff_n * P4V_TILE, s.a, p.d_neg, (float)-p.a_qmax, 0.f};
+      P4VSeg n{s.k0, s.klen, s.xoff_n * P4V_TILE, s.a, p.d_neg, (float)-p.a_qmax, 0.f, 0, 0.f, 0};
       p.segsX.push_back(n);
     }
 

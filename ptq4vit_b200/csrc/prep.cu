@@ -113,8 +113,10 @@ __global__ void quant_image_kernel(const QuantImageArgs a, int chunks_total) {
                    ((size_t)chunk * P4V_TILE + r) * 16;
     uint32_t w[4] = {0u, 0u, 0u, 0u};
     if (row_p < a.rows) {
-      float delta;
-      if (sg.fixed_delta > 0.f) delta = sg.fixed_delta;
+      float delta = 1.f;
+      const float split = sg.sos_part ? (a.factors ? a.factors[plane] : a.split[0]) : 0.f;
+      if (sg.sos_part || sg.split3) { /* step size handled below */ }
+      else if (sg.fixed_delta > 0.f) delta = sg.fixed_delta;
       else {
         const int rb = a.rows_per_block > 0 ? row_p / a.rows_per_block : (p % a.d_mod);
         delta = a.delta[(size_t)rb * a.d_stride + sg.didx];
@@ -128,7 +130,17 @@ __global__ void quant_image_kernel(const QuantImageArgs a, int chunks_total) {
         if (kk < sg.klen) {
           const int k = sg.k0 + kk;
           const float v = a.src_transposed ? base[(size_t)k * a.ld + row_p] : base[(size_t)row_p * a.ld + k];
-          q = fminf(fmaxf(rintf(__fdiv_rn(v, delta)), sg.lo), sg.hi);
+          if (sg.split3) {
+            const float b1 = __bfloat162float(__float2bfloat16_rn(v));
+            const float b2 = __bfloat162float(__float2bfloat16_rn(v - b1));
+            q = sg.split3 == 1 ? b1 : (sg.split3 == 2 ? b2 : __bfloat162float(__float2bfloat16_rn((v - b1) - b2)));
+          } else if (sg.sos_part == 1) {
+            q = fminf(fmaxf(rintf(fminf(fmaxf(v, split), 1.f) * sg.qm1), 0.f), sg.qm1);
+          } else if (sg.sos_part == 2) {
+            q = fminf(fmaxf(rintf(__fdiv_rn(fminf(fmaxf(v, 0.f), split), __fdiv_rn(split, sg.qm1))), 0.f), sg.qm1);
+          } else {
+            q = fminf(fmaxf(rintf(__fdiv_rn(v, delta)), sg.lo), sg.hi);
+          }
           if (!(q == q)) q = 0.f;   // NaN (0/0) cannot be represented in the integer operand
         }
         if constexpr (kInt8) {
@@ -152,8 +164,12 @@ __global__ void step_tables_kernel(const StepTablesArgs a) {
     if (i < total_fix) {
       const int g = i / a.nsg, sg = i % a.nsg;
       const GroupMeta m = a.fixed_meta[g];
-      const int v = min((sg * P4V_CG) / a.crb_rows, a.n_V - 1);
-      a.fix_scale[i] = a.dW[v * a.n_H + m.h] * (m.neg ? a.d_neg : a.dX[m.a]);
+      if (a.kind >= 2) {
+        a.fix_scale[i] = a.dW[sg] * (a.kind == 2 ? a.dX[sg] : a.dX[m.a]);
+      } else {
+        const int v = min((sg * P4V_CG) / a.crb_rows, a.n_V - 1);
+        a.fix_scale[i] = a.dW[v * a.n_H + m.h] * (m.neg ? a.d_neg : a.dX[m.a]);
+      }
     } else if (i < total_fix + total_cb) {
       const int j = i - total_fix;
       const int g = j / a.nsg, sg = j % a.nsg;

@@ -10,6 +10,9 @@ struct P4VSeg {          // one K segment of an operand image
   int didx;              // column index into the step-size table (block / chunk id)
   float fixed_delta;     // > 0: use this constant step size (twin-uniform negative part)
   float lo, hi;          // clamp range
+  int sos_part;          // split-of-softmax twin quantizer (matmul.py:595-598): 1 = high part, 2 = low part, 0 = plain
+  float qm1;             // qmax - 1 for the sos parts
+  int split3;            // 1..3: no quantisation, emit the i-th bf16 term of the exact 3-way split of the fp32 value
 };
 
 struct QuantImageArgs {
@@ -24,6 +27,7 @@ struct QuantImageArgs {
   int d_stride, d_mod;
   const P4VSeg* segs; int nseg;
   int is_int8;
+  const float* split;    // sos: device scalar split point for the current image (candidate planes use factors[plane])
 };
 int p4v_quant_image(const QuantImageArgs& a, cudaStream_t st);
 
@@ -41,7 +45,7 @@ int p4v_make_gscale(const int* key, float* gscale, cudaStream_t st);
 struct GroupMeta { short h, a; short neg; short pad; };   // neg: use the constant negative-part step size
 
 struct StepTablesArgs {
-  int kind;                  // 0: Linear W step, 1: Linear X step, 2: MatMul A step, 3: MatMul B step
+  int kind;                  // 0: Linear W step, 1: Linear X step, 2: head-wise MatMul step, 3: MatMul step whose other operand has per-group uniform scales (sos)
   int target;                // h (W step) / a (X step)
   const float* dW; const float* dW0; int n_V, n_H, crb_rows;
   const float* dX; const float* dX0; int n_a; float d_neg;

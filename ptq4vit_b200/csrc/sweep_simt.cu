@@ -78,7 +78,8 @@ __global__ void __launch_bounds__(256) sweep_simt_kernel(const __grid_constant__
         const uint8_t* cc = ((jb.flags & P4V_JOB_CCAND) ? Ccand : Ccur) + jb.c_off;
         acc += dot_job<kInt8>(rr, cc, row, col, jb.kb);
         if (jb.flags & P4V_JOB_LAST) {
-          const float s = P.candA[(size_t)c * P.nsg + sg] * P.candB[(size_t)jb.group * P.nsg + sg];
+          const float cb = P.candB[(size_t)jb.group * P.nsg + sg];
+          const float s = ((P.cand_noA_mask >> jb.group) & 1ull) ? cb : P.candA[(size_t)c * P.nsg + sg] * cb;
           r = fmaf(-s, acc, r);
         }
       }

@@ -18,6 +18,7 @@
 // Roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 4..11 = epilogue
 // (setmaxnreg moves the register budget of warpgroup 0 to the epilogue warpgroups).
 #include "common.cuh"
+#include <cstdio>
 
 namespace {
 
@@ -55,15 +56,26 @@ __device__ __forceinline__ void mbar_expect_tx(void* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(void* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ bool mbar_try(uint32_t addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\t"
+               "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+               "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a trapped launch (cudaErrorLaunchFailure), never as a hung GPU.
+[[noreturn]] __device__ __noinline__ void mbar_timeout(uint32_t addr, uint32_t parity) {
+  printf("ptq4vit_b200 sweep: mbarrier wait timed out (block %d thread %d smem 0x%x parity %u)\n",
+         (int)blockIdx.x, (int)threadIdx.x, addr, parity);
+  __trap();
+  while (true) {}
+}
 __device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
-  uint32_t addr = smem_u32(bar);
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t}" ::"r"(addr), "r"(parity) : "memory");
+  const uint32_t addr = smem_u32(bar);
+  if (mbar_try(addr, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try(addr, parity))
+    if (clock64() - t0 > 4000000000ll) mbar_timeout(addr, parity);
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, void* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -193,7 +205,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
   Frag f;
 
   if (warp < 4) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
     // ======================= TMA producer =======================
     if (lane == 0) {
@@ -252,7 +264,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
     __syncwarp();
   }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     // ======================= epilogue (8 warps) =======================
     const int ew = warp - 4;                 // 0..7
     const int quarter = warp & 3;            // TMEM lane quarter this warp may access
@@ -368,7 +380,8 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
           tc_fence_after();
           const uint32_t taddr = tmem + lane_addr + kAccCols + slot * kAccCols + hf * 64;
           const float4 cb = *reinterpret_cast<const float4*>(&S.candB[gi][hf * 4]);
-          const float4 sc = make_float4(ca.x * cb.x, ca.y * cb.y, ca.z * cb.z, ca.w * cb.w);
+          const bool noA = (P.cand_noA_mask >> gi) & 1ull;
+          const float4 sc = noA ? cb : make_float4(ca.x * cb.x, ca.y * cb.y, ca.z * cb.z, ca.w * cb.w);
           const bool last = kSingle || (gi == P.n_cand_groups - 1);
 #pragma unroll
           for (int ch = 0; ch < 2; ++ch) {

@@ -51,7 +51,7 @@ def _targmax_spy(inp, *a, **k):
 
 LINEAR_CASES = {
     # name: fixture kwargs, module kwargs
-    "lin_small": dict(fx=dict(seed=11, n_img=8, n_tok=50, K=96, O=96),
+    "lin_small": dict(fx=dict(seed=11, n_img=8, n_tok=50, K=96, O=128),
                       mod=dict(n_V=4, n_H=4, n_a=1, w_bit=8, a_bit=8, search_round=3)),
     "lin_w6a6_na2": dict(fx=dict(seed=12, n_img=6, n_tok=40, K=96, O=192),
                          mod=dict(n_V=4, n_H=4, n_a=2, w_bit=6, a_bit=6, search_round=2)),
