@@ -118,8 +118,14 @@ P4V_API int p4v_matmul_quant_forward(const p4v_matmul_desc* d, const float* A, c
 
 P4V_API const char* p4v_last_error(void);
 P4V_API int p4v_version(void);
-/* number of sweep-kernel launches issued by this process so far (for bench.py's gpu_launches) */
+/* number of kernel launches issued by this library in this process so far (for bench.py's gpu_launches) */
 P4V_API long long p4v_launch_count(void);
+/* Optional live timing of the sweep kernel (bench.py's roofline): while enabled every sweep launch is
+ * bracketed by CUDA events on its own stream.  p4v_profile_collect synchronises those events and returns
+ * the summed device time (ms), the number of sweep launches and the tensor-core operations (2*MAC) they
+ * executed, then clears the record. */
+P4V_API int p4v_profile_enable(int on);
+P4V_API int p4v_profile_collect(double* sweep_ms, long long* sweep_launches, double* executed_ops);
 
 #ifdef __cplusplus
 }

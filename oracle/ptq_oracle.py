@@ -123,7 +123,7 @@ def _hessian_score_linear(raw_out, raw_grad, out_sim, n_groups):
 
 
 def linear_search_w(sp: LinearSpec, W, bias, x, raw_out, raw_grad, w_interval, a_interval, w_cands,
-                    chunk: int = 10):
+                    chunk: int = 10, h_list=None):
     """Greedy per-column-block search of the weight step sizes
     (linear.py:455-495).  w_cands: [eq_n+1,n_V,1,n_H,1].  Returns the new
     w_interval and the list (one per h) of score matrices [eq_n,n_V]."""
@@ -131,7 +131,7 @@ def linear_search_w(sp: LinearSpec, W, bias, x, raw_out, raw_grad, w_interval, a
     x_sim = linear_quant_input(sp, x, a_interval)
     Wv = W.view(sp.n_V, sp.crb_rows, sp.n_H, sp.crb_cols).unsqueeze(0)
     all_scores = []
-    for h in range(sp.n_H):
+    for h in (range(sp.n_H) if h_list is None else h_list):   # h_list: bounded sampling for the CPU baseline
         scores = []
         for p_st in range(0, sp.eq_n, chunk):
             p_ed = min(sp.eq_n, p_st + chunk)

@@ -44,7 +44,7 @@ _SIGNATURES = {
     "p4v_matmul_quant_forward_workspace_bytes": [C.POINTER(MatMulDesc), C.POINTER(C.c_size_t)],
     "p4v_matmul_quant_forward": [C.POINTER(MatMulDesc), _P, _P, _P, _P, _P, _P, C.c_size_t, _P, _P],
 }
-EXPORTS = sorted(list(_SIGNATURES) + ["p4v_last_error", "p4v_version", "p4v_launch_count"])
+EXPORTS = sorted(list(_SIGNATURES) + ["p4v_last_error", "p4v_version", "p4v_launch_count", "p4v_profile_enable", "p4v_profile_collect"])
 
 _lib = None
 
@@ -65,6 +65,8 @@ def lib():
         l.p4v_last_error.restype = C.c_char_p
         l.p4v_version.restype = C.c_int
         l.p4v_launch_count.restype = C.c_longlong
+        l.p4v_profile_enable.argtypes = [C.c_int]
+        l.p4v_profile_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.POINTER(C.c_double)]
         _lib = l
     return _lib
 

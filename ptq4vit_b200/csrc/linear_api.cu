@@ -9,6 +9,8 @@
 #include "../../include/ptq4vit_b200.h"
 #include "prep.cuh"
 
+int p4v_num_sms();
+
 // ---------------------------------------------------------------- error / misc
 static thread_local char g_err[512] = "";
 static long long g_launches = 0;
@@ -20,6 +22,50 @@ extern "C" int p4v_version(void) { return 100; }
 extern "C" long long p4v_launch_count(void) { return g_launches; }
 void p4v_count_launch() { ++g_launches; }
 
+// ---- live sweep timing -------------------------------------------------------
+static bool g_prof = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
+static std::vector<cudaEvent_t> g_prof_pool;
+static double g_prof_ops = 0.0;
+static cudaEvent_t prof_event() {
+  if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+extern "C" int p4v_profile_enable(int on) { g_prof = on != 0; return 0; }
+extern "C" int p4v_profile_collect(double* sweep_ms, long long* sweep_launches, double* executed_ops) {
+  double ms = 0.0;
+  for (auto& pr : g_prof_events) {
+    P4V_CUDA_OK(cudaEventSynchronize(pr.second));
+    float t = 0.f;
+    P4V_CUDA_OK(cudaEventElapsedTime(&t, pr.first, pr.second));
+    ms += t;
+    g_prof_pool.push_back(pr.first); g_prof_pool.push_back(pr.second);
+  }
+  if (sweep_ms) *sweep_ms = ms;
+  if (sweep_launches) *sweep_launches = (long long)g_prof_events.size();
+  if (executed_ops) *executed_ops = g_prof_ops;
+  g_prof_events.clear(); g_prof_ops = 0.0;
+  return 0;
+}
+// tensor-core work of one sweep launch: every job multiplies a 128x128 tile over kb bytes of K
+static double sweep_ops(const SweepParams& sp, const P4VJob* host_jobs) {
+  double kf = 0.0, kc = 0.0;
+  const double ew = sp.is_int8 ? 1.0 : 2.0;
+  for (int j = 0; j < sp.n_fixed_jobs; ++j) kf += host_jobs[j].kb / ew;
+  for (int j = 0; j < sp.n_cand_jobs; ++j) kc += host_jobs[sp.n_fixed_jobs + j].kb / ew;
+  const double tiles = (double)sp.P * sp.tiles_m * sp.tiles_n;
+  return 2.0 * P4V_TILE * P4V_TILE * tiles * (kf + kc * sp.n_cand);
+}
+int p4v_run_sweep(const SweepParams& sp, const P4VJob* host_jobs, int kernel, cudaStream_t st) {
+  ++g_launches;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (g_prof) { e0 = prof_event(); e1 = prof_event(); cudaEventRecord(e0, st); }
+  int rc = kernel == P4V_KERNEL_SIMT ? p4v_launch_sweep_simt(sp, st) : p4v_launch_sweep_tc(sp, p4v_num_sms(), st);
+  if (g_prof) { cudaEventRecord(e1, st); g_prof_events.emplace_back(e0, e1); g_prof_ops += sweep_ops(sp, host_jobs); }
+  return rc;
+}
+
+int p4v_num_sms();
 int p4v_num_sms() {
   static int sms = 0;
   if (sms == 0) {
@@ -281,10 +327,8 @@ void fill_sweep(const LinPlan& p, void* ws, const Step& s, SweepParams& sp) {
   sp.is_int8 = p.i8;
 }
 
-int run_sweep(const LinPlan& p, const SweepParams& sp, cudaStream_t st) {
-  p4v_count_launch();
-  if (p.d.kernel == P4V_KERNEL_SIMT) return p4v_launch_sweep_simt(sp, st);
-  return p4v_launch_sweep_tc(sp, p4v_num_sms(), st);
+int run_sweep(const LinPlan& p, const Step& s, const SweepParams& sp, cudaStream_t st) {
+  return p4v_run_sweep(sp, p.jobs.data() + s.job_off, p.d.kernel, st);
 }
 
 int tables_for(const LinPlan& p, void* ws, const Step& s, int kind, int target, cudaStream_t st) {
@@ -309,7 +353,7 @@ int search_step(const LinPlan& p, void* ws, bool is_w, int idx, const float* bia
   SweepParams sp; fill_sweep(p, ws, s, sp);
   sp.Y = y; sp.Gr = g; sp.bias = p.d.has_bias ? bias : nullptr;
   sp.order = is_w ? 0 : 1;
-  if ((rc = run_sweep(p, sp, st))) return rc;
+  if ((rc = run_sweep(p, s, sp, st))) return rc;
   const int n_groups = is_w ? p.d.n_V : 1;
   ReduceArgs r{};
   r.partial = sp.partial; r.n_cand = p.d.eq_n; r.P = 1; r.tiles_m = p.tiles_m; r.tiles_n = p.tiles_o; r.order = sp.order;
@@ -464,5 +508,5 @@ extern "C" int p4v_linear_quant_forward(const p4v_linear_desc* d, const float* x
   sp.bias = d->has_bias ? bias : nullptr;
   sp.out = out; sp.n_cand = 1; sp.order = 0;
   sp.R_cand = nullptr; sp.C_cand = nullptr;
-  return run_sweep(p, sp, st);
+  return run_sweep(p, p.fwd, sp, st);
 }

@@ -8,7 +8,7 @@
 #include "prep.cuh"
 
 void p4v_count_launch();
-int p4v_num_sms();
+int p4v_run_sweep(const SweepParams& sp, const P4VJob* host_jobs, int kernel, cudaStream_t st);
 
 namespace {
 
@@ -204,10 +204,8 @@ void fill_sweep(const MMPlan& p, void* ws, const MStep& s, SweepParams& sp) {
   sp.n_cand = p.d.eq_n; sp.partial = at<float>(ws, p.o_partial); sp.is_int8 = p.i8;
 }
 
-int run_sweep(const MMPlan& p, const SweepParams& sp, cudaStream_t st) {
-  p4v_count_launch();
-  if (p.d.kernel == P4V_KERNEL_SIMT) return p4v_launch_sweep_simt(sp, st);
-  return p4v_launch_sweep_tc(sp, p4v_num_sms(), st);
+int run_sweep(const MMPlan& p, const MStep& s, const SweepParams& sp, cudaStream_t st) {
+  return p4v_run_sweep(sp, p.jobs.data() + s.job_off, p.d.kernel, st);
 }
 
 // kind 2: searched operand tables (d0, cur other) per head ; kind 3: other operand = aux[meta.a]
@@ -253,7 +251,7 @@ int search_A(const MMPlan& p, void* ws, const float* A, const float* Y, const fl
                    at<float>(ws, p.o_factors), p.d.eq_n, st))) return rc;
   SweepParams sp; fill_sweep(p, ws, p.stepA, sp);
   sp.Y = Y; sp.Gr = G; sp.order = 1;
-  if ((rc = run_sweep(p, sp, st))) return rc;
+  if ((rc = run_sweep(p, p.stepA, sp, st))) return rc;
   if ((rc = reduce_finish(p, ws, sp, p.d.eq_n, p.H, 1.0 / ((double)p.S1 * p.S3), at<float>(ws, p.o_factors),
                           at<float>(ws, p.o_dA0), at<float>(ws, p.o_dA), log, st))) return rc;
   return quant(p, ws, 0, A, st);
@@ -265,7 +263,7 @@ int search_B(const MMPlan& p, void* ws, const float* B, const float* Y, const fl
                    p.sos ? at<float>(ws, p.o_aux) : at<float>(ws, p.o_dA), at<float>(ws, p.o_factors), p.d.eq_n, st))) return rc;
   SweepParams sp; fill_sweep(p, ws, p.stepB, sp);
   sp.Y = Y; sp.Gr = G; sp.order = 0;
-  if ((rc = run_sweep(p, sp, st))) return rc;
+  if ((rc = run_sweep(p, p.stepB, sp, st))) return rc;
   if ((rc = reduce_finish(p, ws, sp, p.d.eq_n, p.H, 1.0 / ((double)p.S1 * p.S3), at<float>(ws, p.o_factors),
                           at<float>(ws, p.o_dB0), at<float>(ws, p.o_dB), log, st))) return rc;
   return quant(p, ws, 2, B, st);
@@ -281,11 +279,12 @@ int search_split(const MMPlan& p, void* ws, const float* A, const float* Y, cons
   sp.R_cand = at<uint8_t>(ws, p.o_Ascand); sp.R_cand_tile_bytes = (unsigned long long)P4V_TILE * p.KB_As;
   sp.R_cand_stride = sp.R_cand_tile_bytes * p.tiles_m * p.P;
   sp.C_cur = at<uint8_t>(ws, p.o_Bsplit); sp.C_tile_bytes = (unsigned long long)P4V_TILE * p.KB_Bs;
-  if ((rc = run_sweep(p, sp, st))) return rc;
+  if ((rc = run_sweep(p, p.stepS, sp, st))) return rc;
   // global score: mean over heads and rows (matmul.py:620-621)
   if ((rc = reduce_finish(p, ws, sp, p.n_split, 1, 1.0 / ((double)p.H * p.S1 * p.S3), at<float>(ws, p.o_sfactors),
                           at<float>(ws, p.o_ones), at<float>(ws, p.o_split), log, st))) return rc;
   sos_aux_kernel<<<1, 1, 0, st>>>(at<float>(ws, p.o_split), (float)(p.A_qmax - 1), at<float>(ws, p.o_aux), nullptr);
+  p4v_count_launch();
   P4V_CUDA_OK(cudaGetLastError());
   return quant(p, ws, 0, A, st);
 }
@@ -397,5 +396,5 @@ extern "C" int p4v_matmul_quant_forward(const p4v_matmul_desc* d, const float* A
                    p.sos ? at<float>(workspace, p.o_aux) : at<float>(workspace, p.o_dB), at<float>(workspace, p.o_factors), 0, st))) return rc;
   SweepParams sp; fill_sweep(p, workspace, p.fwd, sp);
   sp.out = out; sp.n_cand = 1; sp.order = 0; sp.R_cand = nullptr; sp.C_cand = nullptr;
-  return run_sweep(p, sp, st);
+  return run_sweep(p, p.fwd, sp, st);
 }

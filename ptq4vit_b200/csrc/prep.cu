@@ -1,6 +1,8 @@
 #include "prep.cuh"
 #include <math.h>
 
+void p4v_count_launch();
+
 namespace {
 
 // order-preserving float <-> int key (so that atomicMax on ints is max on floats)
@@ -283,7 +285,7 @@ int grid_for(long long total, int block, int cap = 148 * 16) {
 }  // namespace
 
 int p4v_keys_reset(int* keys, int n, cudaStream_t st) {
-  keys_reset_kernel<<<p4v_cdiv(n, 128), 128, 0, st>>>(keys, n);
+  keys_reset_kernel<<<p4v_cdiv(n, 128), 128, 0, st>>>(keys, n); p4v_count_launch();
   P4V_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -296,7 +298,7 @@ int p4v_block_max(const float* src, long long ld, int rows, int row_block, int n
   if (split > 256) split = 256;
   if (split > row_block) split = row_block;
   dim3 grid(split, n_col_blocks, n_row_blocks), block(32, 8);
-  block_max_kernel<<<grid, block, 0, st>>>(src, ld, rows, row_block, col_block, use_abs, keys);
+  block_max_kernel<<<grid, block, 0, st>>>(src, ld, rows, row_block, col_block, use_abs, keys); p4v_count_launch();
   P4V_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -307,19 +309,19 @@ int p4v_group_absmax(const float* src, long long prob_elems, int P, int n_groups
   if (split < 1) split = 1;
   if (split > 128) split = 128;
   dim3 grid(split, n_groups);
-  group_absmax_kernel<<<grid, 256, 0, st>>>(src, prob_elems, P, n_groups, keys);
+  group_absmax_kernel<<<grid, 256, 0, st>>>(src, prob_elems, P, n_groups, keys); p4v_count_launch();
   P4V_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
 int p4v_keys_to_delta(const int* keys, int n, float denom, float* d0, float* d1, cudaStream_t st) {
-  keys_to_delta_kernel<<<p4v_cdiv(n, 128), 128, 0, st>>>(keys, n, denom, d0, d1);
+  keys_to_delta_kernel<<<p4v_cdiv(n, 128), 128, 0, st>>>(keys, n, denom, d0, d1); p4v_count_launch();
   P4V_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
 int p4v_make_gscale(const int* key, float* gscale, cudaStream_t st) {
-  make_gscale_kernel<<<1, 1, 0, st>>>(key, gscale);
+  make_gscale_kernel<<<1, 1, 0, st>>>(key, gscale); p4v_count_launch();
   P4V_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -333,6 +335,7 @@ int p4v_quant_image(const QuantImageArgs& a, cudaStream_t st) {
   const int grid = grid_for(total, 256, 148 * 32);
   if (a.is_int8) quant_image_kernel<true><<<grid, 256, 0, st>>>(a, chunks_total);
   else quant_image_kernel<false><<<grid, 256, 0, st>>>(a, chunks_total);
+  p4v_count_launch();
   P4V_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -340,14 +343,14 @@ int p4v_quant_image(const QuantImageArgs& a, cudaStream_t st) {
 int p4v_step_tables(const StepTablesArgs& a, cudaStream_t st) {
   const int total = (a.n_fixed_groups + a.n_cand_groups + a.n_cand) * a.nsg;
   if (total == 0) return 0;
-  step_tables_kernel<<<grid_for(total, 256, 64), 256, 0, st>>>(a);
+  step_tables_kernel<<<grid_for(total, 256, 64), 256, 0, st>>>(a); p4v_count_launch();
   P4V_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
 int p4v_reduce_scores(const ReduceArgs& a, cudaStream_t st) {
   dim3 grid(a.n_cand, a.n_groups);
-  reduce_scores_kernel<<<grid, 128, 0, st>>>(a);
+  reduce_scores_kernel<<<grid, 128, 0, st>>>(a); p4v_count_launch();
   P4V_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -355,7 +358,7 @@ int p4v_reduce_scores(const ReduceArgs& a, cudaStream_t st) {
 int p4v_finish_step(const FinishArgs& a, cudaStream_t st) {
   const long long total = a.nseg > 0 ? (long long)a.P * a.tiles * P4V_TILE * a.commit_chunks : 0;
   const int grid = grid_for(total, 256, 148 * 8);
-  finish_step_kernel<<<grid, 256, (size_t)a.n_groups * sizeof(int), st>>>(a, a.commit_chunks);
+  finish_step_kernel<<<grid, 256, (size_t)a.n_groups * sizeof(int), st>>>(a, a.commit_chunks); p4v_count_launch();
   P4V_CUDA_OK(cudaGetLastError());
   return 0;
 }
