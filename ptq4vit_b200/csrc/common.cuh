@@ -29,6 +29,7 @@ enum : uint8_t {
   P4V_JOB_LAST   = 2,   // last job of an accumulator group
   P4V_JOB_RCAND  = 4,   // row operand comes from the candidate plane
   P4V_JOB_CCAND  = 8,   // column operand comes from the candidate plane
+  P4V_JOB_RRES   = 16,  // row operand is candidate independent: loaded once per tile fragment (resident), not per job
 };
 
 struct __align__(16) P4VJob {
@@ -37,7 +38,7 @@ struct __align__(16) P4VJob {
   uint16_t kb;         // bytes of K per row (multiple of 32, <= P4V_JOB_KB)
   uint8_t  flags;
   uint8_t  group;      // accumulator group index (row of the scale table)
-  uint32_t pad;
+  uint32_t res_off;    // byte offset inside the resident row-operand buffer (P4V_JOB_RRES)
 };
 
 // score-group mapping of the 16-column groups (used by the sweep for scales and by
@@ -68,6 +69,8 @@ struct SweepParams {
   float* out;               // if non-null: write bias + sum(scale*acc) of the fixed groups (quant_forward), no candidates
   int order;                // 0: tile_m fastest, 1: tile_n fastest
   int is_int8;
+  // shared-memory plan, filled by the launcher
+  unsigned int stage_r_bytes, stage_c_bytes, n_stages, resident_bytes;
 };
 
 static inline __host__ __device__ int p4v_cdiv(int a, int b) { return (a + b - 1) / b; }
@@ -84,5 +87,5 @@ extern "C" void p4v_set_error(const char* fmt, ...);
   do { if (!(cond)) { p4v_set_error(__VA_ARGS__); return 1; } } while (0)
 
 // ---- kernel launchers shared between translation units ----------------------
-int p4v_launch_sweep_tc(const SweepParams& p, int num_sms, cudaStream_t st);
+int p4v_launch_sweep_tc(const SweepParams& p, const P4VJob* host_jobs, int num_sms, cudaStream_t st);
 int p4v_launch_sweep_simt(const SweepParams& p, cudaStream_t st);

@@ -60,7 +60,7 @@ int p4v_run_sweep(const SweepParams& sp, const P4VJob* host_jobs, int kernel, cu
   ++g_launches;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (g_prof) { e0 = prof_event(); e1 = prof_event(); cudaEventRecord(e0, st); }
-  int rc = kernel == P4V_KERNEL_SIMT ? p4v_launch_sweep_simt(sp, st) : p4v_launch_sweep_tc(sp, p4v_num_sms(), st);
+  int rc = kernel == P4V_KERNEL_SIMT ? p4v_launch_sweep_simt(sp, st) : p4v_launch_sweep_tc(sp, host_jobs, p4v_num_sms(), st);
   if (g_prof) { cudaEventRecord(e1, st); g_prof_events.emplace_back(e0, e1); g_prof_ops += sweep_ops(sp, host_jobs); }
   return rc;
 }
@@ -112,6 +112,19 @@ void add_group(LinPlan& p, int r_off_bytes, int c_off_bytes, int kb, uint8_t src
     j.group = (uint8_t)group_idx;
     p.jobs.push_back(j);
     ++njobs;
+  }
+}
+
+// Candidate jobs whose row operand does not depend on the candidate (W steps): keep it resident in shared memory.
+void mark_resident(LinPlan& p, const Step& st) {
+  uint32_t total = 0;
+  for (int j = 0; j < st.ncj; ++j) total += (uint32_t)p.jobs[st.job_off + st.nfj + j].kb * P4V_TILE;
+  if (total == 0 || total > 60 * 1024) return;
+  uint32_t off = 0;
+  for (int j = 0; j < st.ncj; ++j) {
+    P4VJob& jb = p.jobs[st.job_off + st.nfj + j];
+    if (jb.flags & P4V_JOB_RCAND) return;
+    jb.flags |= P4V_JOB_RRES; jb.res_off = off; off += (uint32_t)jb.kb * P4V_TILE;
   }
 }
 
@@ -207,6 +220,7 @@ int build_plan(const p4v_linear_desc* d, LinPlan& p, bool with_search) {
         p.commits.push_back(CommitSeg{s.woff * P4V_TILE, s.woff * P4V_TILE, s.kb});
         st.commit_chunks += s.kb / 16; ++st.ncommit;
       }
+      mark_resident(p, st);
       p.wsteps.push_back(st);
     }
     for (int a = 0; a < d->n_a; ++a) {
@@ -247,7 +261,7 @@ int build_plan(const p4v_linear_desc* d, LinPlan& p, bool with_search) {
   p.o_dW0 = take(d->n_V * d->n_H * 4); p.o_dW = take(d->n_V * d->n_H * 4);
   p.o_dX0 = take(d->n_a * 4); p.o_dX = take(d->n_a * 4);
   p.o_gscale = take(4);
-  p.o_scores = take((size_t)n_c * std::max(d->n_V, 1) * 8);
+  p.o_scores = take((size_t)n_c * p.nsg * 8);
   p.o_best = take(std::max(d->n_V, 1) * 4);
   p.o_fix = take((size_t)p.max_groups * p.nsg * 4);
   p.o_candA = take((size_t)n_c * p.nsg * 4);
@@ -331,9 +345,9 @@ int run_sweep(const LinPlan& p, const Step& s, const SweepParams& sp, cudaStream
   return p4v_run_sweep(sp, p.jobs.data() + s.job_off, p.d.kernel, st);
 }
 
-int tables_for(const LinPlan& p, void* ws, const Step& s, int kind, int target, cudaStream_t st) {
+StepTablesArgs tables_args(const LinPlan& p, void* ws, const Step& s, int kind, int target) {
   StepTablesArgs t{};
-  t.kind = kind; t.target = target;
+  t.kind = kind < 0 ? 0 : kind; t.target = target;
   t.dW = at<float>(ws, p.o_dW); t.dW0 = at<float>(ws, p.o_dW0); t.n_V = p.d.n_V; t.n_H = p.d.n_H; t.crb_rows = p.crb_rows;
   t.dX = at<float>(ws, p.o_dX); t.dX0 = at<float>(ws, p.o_dX0); t.n_a = p.d.n_a; t.d_neg = p.d_neg;
   t.factors = at<float>(ws, p.o_factors); t.n_cand = kind < 0 ? 0 : p.d.eq_n;
@@ -341,15 +355,22 @@ int tables_for(const LinPlan& p, void* ws, const Step& s, int kind, int target, 
   t.cand_meta = at<GroupMeta>(ws, p.o_metas) + s.meta_cand; t.n_cand_groups = s.ncg;
   t.nsg = p.nsg;
   t.fix_scale = at<float>(ws, p.o_fix); t.candA = at<float>(ws, p.o_candA); t.candB = at<float>(ws, p.o_candB);
-  if (kind < 0) t.kind = 0;
-  return p4v_step_tables(t, st);
+  return t;
 }
 
-int search_step(const LinPlan& p, void* ws, bool is_w, int idx, const float* bias, const float* y, const float* g,
-                float* score_log, cudaStream_t st) {
+int tables_for(const LinPlan& p, void* ws, const Step& s, int kind, int target, cudaStream_t st) {
+  return p4v_step_tables(tables_args(p, ws, s, kind, target), st);
+}
+
+struct StepRef { bool is_w; int idx; };
+
+// One search step: [scale tables] -> sweep -> reduce -> select (+ tables of the next step) -> commit.
+int search_step(const LinPlan& p, void* ws, StepRef cur, const StepRef* next, bool tables_ready, const float* bias,
+                const float* y, const float* g, float* score_log, cudaStream_t st) {
+  const bool is_w = cur.is_w; const int idx = cur.idx;
   const Step& s = is_w ? p.wsteps[idx] : p.xsteps[idx];
   int rc;
-  if ((rc = tables_for(p, ws, s, is_w ? 0 : 1, idx, st))) return rc;
+  if (!tables_ready && (rc = tables_for(p, ws, s, is_w ? 0 : 1, idx, st))) return rc;
   SweepParams sp; fill_sweep(p, ws, s, sp);
   sp.Y = y; sp.Gr = g; sp.bias = p.d.has_bias ? bias : nullptr;
   sp.order = is_w ? 0 : 1;
@@ -357,24 +378,30 @@ int search_step(const LinPlan& p, void* ws, bool is_w, int idx, const float* bia
   const int n_groups = is_w ? p.d.n_V : 1;
   ReduceArgs r{};
   r.partial = sp.partial; r.n_cand = p.d.eq_n; r.P = 1; r.tiles_m = p.tiles_m; r.tiles_n = p.tiles_o; r.order = sp.order;
-  r.mode = P4V_SG_COLUMN; r.n_groups = n_groups; r.cg_per_group = is_w ? p.crb_rows / P4V_CG : p.nsg;
-  r.inv_count = 1.0 / ((double)p.d.tokens * (double)(is_w ? p.crb_rows : p.O));
-  r.gscale = at<float>(ws, p.o_gscale); r.scores = at<double>(ws, p.o_scores);
+  r.mode = P4V_SG_COLUMN; r.n_keys = p.nsg; r.sums = at<double>(ws, p.o_scores);
   if ((rc = p4v_reduce_scores(r, st))) return rc;
-  FinishArgs f{};
-  f.scores = r.scores; f.n_cand = p.d.eq_n; f.n_groups = n_groups; f.factors = at<float>(ws, p.o_factors);
+  SelectArgs f{};
+  f.sums = r.sums; f.n_cand = p.d.eq_n; f.n_keys = p.nsg; f.n_groups = n_groups;
+  f.keys_per_group = (is_w && p.d.n_V > 1) ? p.crb_rows / P4V_CG : p.nsg;
+  f.inv_count = 1.0 / ((double)p.d.tokens * (double)(is_w ? p.crb_rows : p.O));
+  f.gscale = at<float>(ws, p.o_gscale); f.factors = at<float>(ws, p.o_factors);
   if (is_w) { f.d0 = at<float>(ws, p.o_dW0); f.d = at<float>(ws, p.o_dW); f.d_stride = p.d.n_H; f.d_col = idx; }
   else      { f.d0 = at<float>(ws, p.o_dX0); f.d = at<float>(ws, p.o_dX); f.d_stride = 0; f.d_col = idx; }
   f.best = at<int>(ws, p.o_best); f.score_log = score_log;
-  f.cand = at<uint8_t>(ws, is_w ? p.o_Wcand : p.o_Xcand);
-  f.cand_tile_bytes = (unsigned long long)P4V_TILE * (is_w ? p.KB_W : p.KB_Xc);
-  f.cand_plane_stride = f.cand_tile_bytes * (is_w ? p.tiles_o : p.tiles_m);
-  f.cur = at<uint8_t>(ws, is_w ? p.o_Wcur : p.o_Xcur);
-  f.cur_tile_bytes = (unsigned long long)P4V_TILE * (is_w ? p.KB_W : p.KB_X);
-  f.P = 1; f.rows = is_w ? p.O : p.M; f.tiles = is_w ? p.tiles_o : p.tiles_m;
-  f.rows_per_group = is_w ? p.crb_rows : 0; f.problem_groups = 0;
-  f.segs = at<CommitSeg>(ws, p.o_commits) + s.commit_off; f.nseg = s.ncommit; f.commit_chunks = s.commit_chunks;
-  return p4v_finish_step(f, st);
+  f.has_next = next != nullptr;
+  if (next) f.next = tables_args(p, ws, next->is_w ? p.wsteps[next->idx] : p.xsteps[next->idx], next->is_w ? 0 : 1, next->idx);
+  if ((rc = p4v_select_step(f, st))) return rc;
+  CommitArgs c{};
+  c.best = f.best; c.n_groups = n_groups;
+  c.cand = at<uint8_t>(ws, is_w ? p.o_Wcand : p.o_Xcand);
+  c.cand_tile_bytes = (unsigned long long)P4V_TILE * (is_w ? p.KB_W : p.KB_Xc);
+  c.cand_plane_stride = c.cand_tile_bytes * (is_w ? p.tiles_o : p.tiles_m);
+  c.cur = at<uint8_t>(ws, is_w ? p.o_Wcur : p.o_Xcur);
+  c.cur_tile_bytes = (unsigned long long)P4V_TILE * (is_w ? p.KB_W : p.KB_X);
+  c.P = 1; c.tiles = is_w ? p.tiles_o : p.tiles_m;
+  c.rows_per_group = is_w ? p.crb_rows : 0; c.problem_groups = 0;
+  c.segs = at<CommitSeg>(ws, p.o_commits) + s.commit_off; c.nseg = s.ncommit; c.commit_chunks = s.commit_chunks;
+  return p4v_commit_step(c, st);
 }
 
 int begin_impl(const LinPlan& p, const float* x, const float* W, const float* g, void* ws, cudaStream_t st) {
@@ -429,7 +456,9 @@ extern "C" int p4v_linear_search_w(const p4v_linear_desc* d, const float* bias, 
   P4V_REQUIRE(raw_out && raw_grad && workspace, "linear_search_w: null pointer");
   P4V_REQUIRE(0 <= h_begin && h_begin <= h_end && h_end <= d->n_H, "linear_search_w: bad block range");
   for (int h = h_begin; h < h_end; ++h) {
-    if ((rc = search_step(p, workspace, true, h, bias, raw_out, raw_grad, score_log, (cudaStream_t)stream))) return rc;
+    StepRef nx{true, h + 1};
+    if ((rc = search_step(p, workspace, StepRef{true, h}, h + 1 < h_end ? &nx : nullptr, h > h_begin, bias, raw_out, raw_grad,
+                          score_log, (cudaStream_t)stream))) return rc;
     if (score_log) score_log += (size_t)d->eq_n * d->n_V;
   }
   return 0;
@@ -442,7 +471,9 @@ extern "C" int p4v_linear_search_a(const p4v_linear_desc* d, const float* bias, 
   P4V_REQUIRE(raw_out && raw_grad && workspace, "linear_search_a: null pointer");
   P4V_REQUIRE(0 <= a_begin && a_begin <= a_end && a_end <= d->n_a, "linear_search_a: bad chunk range");
   for (int a = a_begin; a < a_end; ++a) {
-    if ((rc = search_step(p, workspace, false, a, bias, raw_out, raw_grad, score_log, (cudaStream_t)stream))) return rc;
+    StepRef nx{false, a + 1};
+    if ((rc = search_step(p, workspace, StepRef{false, a}, a + 1 < a_end ? &nx : nullptr, a > a_begin, bias, raw_out, raw_grad,
+                          score_log, (cudaStream_t)stream))) return rc;
     if (score_log) score_log += d->eq_n;
   }
   return 0;
@@ -467,15 +498,15 @@ extern "C" int p4v_linear_calibrate(const p4v_linear_desc* d, const float* x, co
   P4V_REQUIRE(workspace_bytes >= p.total, "linear_calibrate: workspace too small (%zu < %zu)", workspace_bytes, p.total);
   cudaStream_t st = (cudaStream_t)stream;
   if ((rc = begin_impl(p, x, weight, raw_grad, workspace, st))) return rc;
+  std::vector<StepRef> seq;
   for (int e = 0; e < d->search_round; ++e) {
-    for (int h = 0; h < d->n_H; ++h) {
-      if ((rc = search_step(p, workspace, true, h, bias, raw_out, raw_grad, score_log, st))) return rc;
-      if (score_log) score_log += (size_t)d->eq_n * d->n_V;
-    }
-    for (int a = 0; a < d->n_a; ++a) {
-      if ((rc = search_step(p, workspace, false, a, bias, raw_out, raw_grad, score_log, st))) return rc;
-      if (score_log) score_log += d->eq_n;
-    }
+    for (int h = 0; h < d->n_H; ++h) seq.push_back(StepRef{true, h});
+    for (int a = 0; a < d->n_a; ++a) seq.push_back(StepRef{false, a});
+  }
+  for (size_t i = 0; i < seq.size(); ++i) {
+    if ((rc = search_step(p, workspace, seq[i], i + 1 < seq.size() ? &seq[i + 1] : nullptr, i > 0, bias, raw_out, raw_grad,
+                          score_log, st))) return rc;
+    if (score_log) score_log += seq[i].is_w ? (size_t)d->eq_n * d->n_V : (size_t)d->eq_n;
   }
   P4V_CUDA_OK(cudaMemcpyAsync(w_interval, at<float>(workspace, p.o_dW), (size_t)d->n_V * d->n_H * 4, cudaMemcpyDeviceToDevice, st));
   P4V_CUDA_OK(cudaMemcpyAsync(a_interval, at<float>(workspace, p.o_dX), (size_t)d->n_a * 4, cudaMemcpyDeviceToDevice, st));

@@ -111,6 +111,15 @@ int build_plan(const p4v_matmul_desc* d, MMPlan& p, bool with_search) {
         p.metas.push_back(GroupMeta{0, (short)part, 0, 0}); ++p.stepB.ncg;     // aux[0] = 1/(qmax-1), aux[1] = A_interval
       }
     }
+    {   // the row operand (A) of the B step is the same for every candidate: keep it resident when it is small
+      uint32_t total = 0, off = 0;
+      for (int j = 0; j < p.stepB.ncj; ++j) total += (uint32_t)p.jobs[p.stepB.job_off + j].kb * P4V_TILE;
+      if (total <= 60 * 1024)
+        for (int j = 0; j < p.stepB.ncj; ++j) {
+          P4VJob& jb = p.jobs[p.stepB.job_off + j];
+          jb.flags |= P4V_JOB_RRES; jb.res_off = off; off += (uint32_t)jb.kb * P4V_TILE;
+        }
+    }
   }
   begin(p.fwd);
   if (!p.sos) { push_jobs(p, 0, 0, p.kb, 0, 0, true, true, p.fwd.nfj); p.metas.push_back(GroupMeta{0, 0, 0, 0}); p.fwd.nfg = 1; }
@@ -234,15 +243,15 @@ int reduce_finish(const MMPlan& p, void* ws, const SweepParams& sp, int n_cand, 
                   const float* factors, const float* d0, float* d, float* score_log, cudaStream_t st) {
   ReduceArgs r{};
   r.partial = sp.partial; r.n_cand = n_cand; r.P = p.P; r.tiles_m = p.tiles_m; r.tiles_n = p.tiles_n; r.order = sp.order;
-  r.mode = n_groups == 1 ? P4V_SG_COLUMN : P4V_SG_PROBLEM; r.n_groups = n_groups; r.cg_per_group = p.tiles_n * P4V_TILE_CG;
-  r.inv_count = inv_count; r.gscale = at<float>(ws, p.o_gscale); r.scores = at<double>(ws, p.o_scores);
+  r.mode = P4V_SG_PROBLEM; r.n_keys = p.H; r.sums = at<double>(ws, p.o_scores);
   int rc = p4v_reduce_scores(r, st);
   if (rc) return rc;
-  FinishArgs f{};     // no image commit: the current image is re-quantised from the fp32 source with the chosen step size
-  f.scores = r.scores; f.n_cand = n_cand; f.n_groups = n_groups; f.factors = factors;
+  SelectArgs f{};     // no image commit: the current image is re-quantised from the fp32 source with the chosen step size
+  f.sums = r.sums; f.n_cand = n_cand; f.n_keys = p.H; f.n_groups = n_groups; f.keys_per_group = n_groups == 1 ? p.H : 1;
+  f.inv_count = inv_count; f.gscale = at<float>(ws, p.o_gscale); f.factors = factors;
   f.d0 = d0; f.d = d; f.d_stride = 1; f.d_col = 0; f.best = at<int>(ws, p.o_best); f.score_log = score_log;
-  f.P = p.P; f.segs = nullptr; f.nseg = 0; f.commit_chunks = 0;
-  return p4v_finish_step(f, st);
+  f.has_next = 0;
+  return p4v_select_step(f, st);
 }
 
 int search_A(const MMPlan& p, void* ws, const float* A, const float* Y, const float* G, float* log, cudaStream_t st) {

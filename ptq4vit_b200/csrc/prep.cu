@@ -88,81 +88,88 @@ __global__ void make_gscale_kernel(const int* key, float* gscale) {
   gscale[0] = s;
 }
 
-// One thread = one (plane, problem, padded row, 16-byte chunk of one segment).
+// One thread = one (plane, problem, 16-byte chunk, padded row).  grid = (row blocks, P * chunks, planes): rows are
+// the fastest index so that the 16-byte stores of a warp are contiguous in the image.
 template <bool kInt8>
 __global__ void quant_image_kernel(const QuantImageArgs a, int chunks_total) {
-  const long long rows_pad = (long long)a.tiles * P4V_TILE;
-  const long long per_plane = (long long)a.P * rows_pad * chunks_total;
-  const long long total = per_plane * a.n_planes;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    // row fastest so that the 16-byte stores of a warp are contiguous
-    const int plane = (int)(idx / per_plane);
-    long long rem = idx % per_plane;
-    const int row_p = (int)(rem % rows_pad); rem /= rows_pad;
-    const int chunk_g = (int)(rem % chunks_total);
-    const int p = (int)(rem / chunks_total);
-    // find the segment of this chunk
-    int s = 0, chunk = chunk_g;
-    constexpr int epc = kInt8 ? 16 : 8;          // elements per 16-byte chunk
-    while (true) {
-      const int nch = ((a.segs[s].klen + (kInt8 ? 31 : 15)) / (kInt8 ? 32 : 16)) * 2;   // chunks of this segment (padded to 32 B)
-      if (chunk < nch) break;
-      chunk -= nch; ++s;
+  const int rows_pad = a.tiles * P4V_TILE;
+  const int row_p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row_p >= rows_pad) return;
+  const int plane = blockIdx.z;
+  const int p = blockIdx.y / chunks_total;
+  int chunk = blockIdx.y % chunks_total;
+  constexpr int epc = kInt8 ? 16 : 8;          // elements per 16-byte chunk
+  int s = 0;
+  while (true) {
+    const int nch = ((a.segs[s].klen + (kInt8 ? 31 : 15)) / (kInt8 ? 32 : 16)) * 2;   // chunks of this segment (padded to 32 B)
+    if (chunk < nch) break;
+    chunk -= nch; ++s;
+  }
+  const P4VSeg sg = a.segs[s];
+  const int tile = row_p / P4V_TILE, r = row_p % P4V_TILE;
+  uint8_t* dst = a.dst + (size_t)plane * a.plane_stride + ((size_t)p * a.tiles + tile) * a.tile_bytes + sg.dst_off +
+                 ((size_t)chunk * P4V_TILE + r) * 16;
+  uint32_t w[4] = {0u, 0u, 0u, 0u};
+  if (row_p < a.rows) {
+    float delta = 1.f;
+    const float split = sg.sos_part ? (a.factors ? a.factors[plane] : a.split[0]) : 0.f;
+    if (sg.sos_part || sg.split3) { /* step size handled below */ }
+    else if (sg.fixed_delta > 0.f) delta = sg.fixed_delta;
+    else {
+      const int rb = a.rows_per_block > 0 ? row_p / a.rows_per_block : (p % a.d_mod);
+      delta = a.delta[(size_t)rb * a.d_stride + sg.didx];
+      if (a.factors) delta = a.factors[plane] * delta;       // fl(f_c * delta0), as the reference's candidate table
     }
-    const P4VSeg sg = a.segs[s];
-    const int tile = row_p / P4V_TILE, r = row_p % P4V_TILE;
-    uint8_t* dst = a.dst + (size_t)plane * a.plane_stride + ((size_t)p * a.tiles + tile) * a.tile_bytes + sg.dst_off +
-                   ((size_t)chunk * P4V_TILE + r) * 16;
-    uint32_t w[4] = {0u, 0u, 0u, 0u};
-    if (row_p < a.rows) {
-      float delta = 1.f;
-      const float split = sg.sos_part ? (a.factors ? a.factors[plane] : a.split[0]) : 0.f;
-      if (sg.sos_part || sg.split3) { /* step size handled below */ }
-      else if (sg.fixed_delta > 0.f) delta = sg.fixed_delta;
-      else {
-        const int rb = a.rows_per_block > 0 ? row_p / a.rows_per_block : (p % a.d_mod);
-        delta = a.delta[(size_t)rb * a.d_stride + sg.didx];
-        if (a.factors) delta = a.factors[plane] * delta;       // fl(f_c * delta0), as the reference's candidate table
-      }
-      const float* base = a.src + (size_t)p * a.prob_stride;
+    const float* base = a.src + (size_t)p * a.prob_stride;
+    float vals[epc];
+    if (!a.src_transposed && chunk * epc + epc <= sg.klen && ((a.ld | sg.k0) & 3) == 0) {
+      const float4* src4 = reinterpret_cast<const float4*>(base + (size_t)row_p * a.ld + sg.k0 + chunk * epc);
+#pragma unroll
+      for (int e = 0; e < epc / 4; ++e) { const float4 t4 = src4[e]; vals[4 * e] = t4.x; vals[4 * e + 1] = t4.y; vals[4 * e + 2] = t4.z; vals[4 * e + 3] = t4.w; }
+    } else {
 #pragma unroll
       for (int e = 0; e < epc; ++e) {
         const int kk = chunk * epc + e;
-        float q = 0.f;
-        if (kk < sg.klen) {
-          const int k = sg.k0 + kk;
-          const float v = a.src_transposed ? base[(size_t)k * a.ld + row_p] : base[(size_t)row_p * a.ld + k];
-          if (sg.split3) {
-            const float b1 = __bfloat162float(__float2bfloat16_rn(v));
-            const float b2 = __bfloat162float(__float2bfloat16_rn(v - b1));
-            q = sg.split3 == 1 ? b1 : (sg.split3 == 2 ? b2 : __bfloat162float(__float2bfloat16_rn((v - b1) - b2)));
-          } else if (sg.sos_part == 1) {
-            q = fminf(fmaxf(rintf(fminf(fmaxf(v, split), 1.f) * sg.qm1), 0.f), sg.qm1);
-          } else if (sg.sos_part == 2) {
-            q = fminf(fmaxf(rintf(__fdiv_rn(fminf(fmaxf(v, 0.f), split), __fdiv_rn(split, sg.qm1))), 0.f), sg.qm1);
-          } else {
-            q = fminf(fmaxf(rintf(__fdiv_rn(v, delta)), sg.lo), sg.hi);
-          }
-          if (!(q == q)) q = 0.f;   // NaN (0/0) cannot be represented in the integer operand
-        }
-        if constexpr (kInt8) {
-          const int qi = (int)q;
-          w[e >> 2] |= (uint32_t)(qi & 0xff) << ((e & 3) * 8);
-        } else {
-          const uint32_t hb = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(q));
-          w[e >> 1] |= hb << ((e & 1) * 16);
-        }
+        const int k = sg.k0 + kk;
+        vals[e] = kk < sg.klen ? (a.src_transposed ? base[(size_t)k * a.ld + row_p] : base[(size_t)row_p * a.ld + k]) : 0.f;
       }
     }
-    *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+#pragma unroll
+    for (int e = 0; e < epc; ++e) {
+      const int kk = chunk * epc + e;
+      float q = 0.f;
+      if (kk < sg.klen) {
+        const float v = vals[e];
+        if (sg.split3) {
+          const float b1 = __bfloat162float(__float2bfloat16_rn(v));
+          const float b2 = __bfloat162float(__float2bfloat16_rn(v - b1));
+          q = sg.split3 == 1 ? b1 : (sg.split3 == 2 ? b2 : __bfloat162float(__float2bfloat16_rn((v - b1) - b2)));
+        } else if (sg.sos_part == 1) {
+          q = fminf(fmaxf(rintf(fminf(fmaxf(v, split), 1.f) * sg.qm1), 0.f), sg.qm1);
+        } else if (sg.sos_part == 2) {
+          q = fminf(fmaxf(rintf(__fdiv_rn(fminf(fmaxf(v, 0.f), split), __fdiv_rn(split, sg.qm1))), 0.f), sg.qm1);
+        } else {
+          q = fminf(fmaxf(rintf(__fdiv_rn(v, delta)), sg.lo), sg.hi);
+        }
+        if (!(q == q)) q = 0.f;   // NaN (0/0) cannot be represented in the integer operand
+      }
+      if constexpr (kInt8) {
+        const int qi = (int)q;
+        w[e >> 2] |= (uint32_t)(qi & 0xff) << ((e & 3) * 8);
+      } else {
+        const uint32_t hb = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(q));
+        w[e >> 1] |= hb << ((e & 1) * 16);
+      }
+    }
   }
+  *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-__global__ void step_tables_kernel(const StepTablesArgs a) {
+__device__ __forceinline__ void step_tables_body(const StepTablesArgs& a, int tid, int nthreads) {
   const int total_fix = a.n_fixed_groups * a.nsg;
   const int total_cb = a.n_cand_groups * a.nsg;
   const int total_ca = a.n_cand * a.nsg;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total_fix + total_cb + total_ca; i += gridDim.x * blockDim.x) {
+  for (int i = tid; i < total_fix + total_cb + total_ca; i += nthreads) {
     if (i < total_fix) {
       const int g = i / a.nsg, sg = i % a.nsg;
       const GroupMeta m = a.fixed_meta[g];
@@ -193,70 +200,80 @@ __global__ void step_tables_kernel(const StepTablesArgs a) {
     }
   }
 }
+__global__ void step_tables_kernel(const StepTablesArgs a) {
+  step_tables_body(a, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+}
 
-// grid (n_cand, n_groups), 128 threads.  Fixed item order + fixed tree => deterministic.
+// One warp per (candidate, key): coalesced 128-byte rows of the partial buffer, fixed order, fp64.
 __global__ void reduce_scores_kernel(const ReduceArgs a) {
-  const int c = blockIdx.x, g = blockIdx.y;
+  const int warps_per_block = blockDim.x >> 5;
+  const int task = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int n_task_keys = a.mode == P4V_SG_COLUMN ? a.tiles_n : a.n_keys;
+  if (task >= a.n_cand * n_task_keys) return;
+  const int c = task / n_task_keys, key = task % n_task_keys;
   const int per_p = a.tiles_m * a.tiles_n;
   double acc = 0.0;
-  if (a.mode == P4V_SG_COLUMN) {
-    const int ncg = a.tiles_n * P4V_TILE_CG;
-    const int cg0 = a.n_groups == 1 ? 0 : g * a.cg_per_group;
-    const int cg1 = a.n_groups == 1 ? ncg : min(ncg, cg0 + a.cg_per_group);
-    const int ncgs = cg1 - cg0;
-    const long long items = (long long)a.P * a.tiles_m * 4 * ncgs;
-    for (long long i = threadIdx.x; i < items; i += blockDim.x) {
-      const int cgl = (int)(i % ncgs); long long r = i / ncgs;
-      const int q = (int)(r % 4); r /= 4;
-      const int tm = (int)(r % a.tiles_m); const int p = (int)(r / a.tiles_m);
-      const int cg = cg0 + cgl, tn = cg >> 3, i8 = cg & 7;
-      const int t = a.order == 0 ? tn * a.tiles_m + tm : tm * a.tiles_n + tn;
-      acc += (double)a.partial[(((size_t)p * per_p + t) * a.n_cand + c) * 32 + q * 8 + i8];
-    }
-  } else {
-    const int np = (a.P - g + a.n_groups - 1) / a.n_groups;     // problems p = g + k*n_groups
-    const long long items = (long long)np * per_p * 32;
-    for (long long i = threadIdx.x; i < items; i += blockDim.x) {
-      const int e = (int)(i % 32); long long r = i / 32;
-      const int t = (int)(r % per_p); const int k = (int)(r / per_p);
-      const int p = g + k * a.n_groups;
-      acc += (double)a.partial[(((size_t)p * per_p + t) * a.n_cand + c) * 32 + e];
-    }
-  }
-  __shared__ double red[128];
-  red[threadIdx.x] = acc;
-  __syncthreads();
-  for (int o = 64; o > 0; o >>= 1) {
-    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    const double gs = (double)a.gscale[0];
-    a.scores[(size_t)c * a.n_groups + g] = -red[0] * a.inv_count / (gs * gs);
+  if (a.mode == P4V_SG_COLUMN) {          // key = tn ; lane = quarter * 8 + i8
+    for (int p = 0; p < a.P; ++p)
+      for (int tm = 0; tm < a.tiles_m; ++tm) {
+        const int t = a.order == 0 ? key * a.tiles_m + tm : tm * a.tiles_n + key;
+        acc += (double)a.partial[(((size_t)p * per_p + t) * a.n_cand + c) * 32 + lane];
+      }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+    if (lane < 8) a.sums[(size_t)c * a.n_keys + key * P4V_TILE_CG + lane] = acc;
+  } else {                                // key = p % n_keys ; all 32 entries belong to the key
+    for (int p = key; p < a.P; p += a.n_keys)
+      for (int t = 0; t < per_p; ++t)
+        acc += (double)a.partial[(((size_t)p * per_p + t) * a.n_cand + c) * 32 + lane];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) a.sums[(size_t)c * a.n_keys + key] = acc;
   }
 }
 
-// Every block recomputes the (tiny) argmax table; block 0 publishes the new step sizes;
-// all blocks copy the winning candidate's image slabs into the current image.
-__global__ void finish_step_kernel(const FinishArgs a, int chunks_total) {
-  extern __shared__ int s_best[];
-  for (int g = threadIdx.x; g < a.n_groups; g += blockDim.x) {
-    int bi = 0; double bv = a.scores[g];
-    for (int c = 1; c < a.n_cand; ++c) {
-      const double v = a.scores[(size_t)c * a.n_groups + g];
-      if (v > bv || (v != v && bv == bv)) { bv = v; bi = c; }     // first maximum; NaN wins like torch.argmax
+__global__ void __launch_bounds__(1024) select_step_kernel(const SelectArgs a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const double gs = (double)a.gscale[0];
+  const double norm = a.inv_count / (gs * gs);
+  for (int g = warp; g < a.n_groups; g += nwarps) {
+    double bv = 0.0; int bi = -1;
+    for (int c = lane; c < a.n_cand; c += 32) {      // ascending c: strict '>' keeps the first maximum
+      double sacc = 0.0;
+      for (int k = 0; k < a.keys_per_group; ++k) sacc += a.sums[(size_t)c * a.n_keys + g * a.keys_per_group + k];
+      const double v = -sacc * norm;
+      if (a.score_log) a.score_log[(size_t)c * a.n_groups + g] = (float)v;
+      bool take;
+      if (bi < 0) take = true;
+      else if (bv != bv) take = false;               // an earlier NaN already won
+      else take = (v != v) || (v > bv);
+      if (take) { bv = v; bi = c; }
     }
-    s_best[g] = bi;
-    if (blockIdx.x == 0) {
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      bool take;
+      if (oi < 0) take = false;
+      else if (bi < 0) take = true;
+      else if ((ov != ov) != (bv != bv)) take = (ov != ov);                // NaN beats a number
+      else if (ov != ov) take = oi < bi;                                   // both NaN: lower index
+      else take = ov > bv || (ov == bv && oi < bi);
+      if (take) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) {
       const size_t di = (size_t)g * a.d_stride + a.d_col;
       a.d[di] = a.factors[bi] * a.d0[di];
-      if (a.best) a.best[g] = bi;
+      a.best[g] = bi;
     }
   }
-  if (blockIdx.x == 0 && a.score_log)
-    for (int i = threadIdx.x; i < a.n_cand * a.n_groups; i += blockDim.x) a.score_log[i] = (float)a.scores[i];
-  __syncthreads();
-  if (a.nseg == 0) return;
+  if (a.has_next) {
+    __threadfence_block();
+    __syncthreads();
+    step_tables_body(a.next, threadIdx.x, blockDim.x);
+  }
+}
+
+__global__ void commit_step_kernel(const CommitArgs a, int chunks_total) {
   const long long rows_pad = (long long)a.tiles * P4V_TILE;
   const long long total = (long long)a.P * rows_pad * chunks_total;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -269,7 +286,7 @@ __global__ void finish_step_kernel(const FinishArgs a, int chunks_total) {
     else if (a.rows_per_group > 0) g = min(row_p / a.rows_per_group, a.n_groups - 1);
     const int tile = row_p / P4V_TILE, r = row_p % P4V_TILE;
     const size_t in_tile = ((size_t)chunk * P4V_TILE + r) * 16;
-    const uint4 v = *reinterpret_cast<const uint4*>(a.cand + (size_t)s_best[g] * a.cand_plane_stride +
+    const uint4 v = *reinterpret_cast<const uint4*>(a.cand + (size_t)a.best[g] * a.cand_plane_stride +
                                                    ((size_t)p * a.tiles + tile) * a.cand_tile_bytes + a.segs[s].src_off + in_tile);
     *reinterpret_cast<uint4*>(a.cur + ((size_t)p * a.tiles + tile) * a.cur_tile_bytes + a.segs[s].dst_off + in_tile) = v;
   }
@@ -327,14 +344,13 @@ int p4v_make_gscale(const int* key, float* gscale, cudaStream_t st) {
 }
 
 int p4v_quant_image(const QuantImageArgs& a, cudaStream_t st) {
-  // chunk count per row over all segments (host copy of the seg table is not available here:
-  // the caller passes tile_bytes = 128 * padded bytes, and every segment is padded to 32 B)
-  const int chunks_total = (int)(a.tile_bytes / P4V_TILE / 16);
-  const long long total = (long long)a.n_planes * a.P * a.tiles * P4V_TILE * chunks_total;
-  if (total == 0) return 0;
-  const int grid = grid_for(total, 256, 148 * 32);
-  if (a.is_int8) quant_image_kernel<true><<<grid, 256, 0, st>>>(a, chunks_total);
-  else quant_image_kernel<false><<<grid, 256, 0, st>>>(a, chunks_total);
+  const int chunks_total = (int)(a.tile_bytes / P4V_TILE / 16);     // every segment is padded to 32 B
+  const int rows_pad = a.tiles * P4V_TILE;
+  if (rows_pad == 0 || chunks_total == 0 || a.n_planes == 0 || a.P == 0) return 0;
+  P4V_REQUIRE((long long)a.P * chunks_total <= 65535 && a.n_planes <= 65535, "quant_image: grid too large");
+  dim3 grid(p4v_cdiv(rows_pad, 128), a.P * chunks_total, a.n_planes);
+  if (a.is_int8) quant_image_kernel<true><<<grid, 128, 0, st>>>(a, chunks_total);
+  else quant_image_kernel<false><<<grid, 128, 0, st>>>(a, chunks_total);
   p4v_count_launch();
   P4V_CUDA_OK(cudaGetLastError());
   return 0;
@@ -349,16 +365,25 @@ int p4v_step_tables(const StepTablesArgs& a, cudaStream_t st) {
 }
 
 int p4v_reduce_scores(const ReduceArgs& a, cudaStream_t st) {
-  dim3 grid(a.n_cand, a.n_groups);
-  reduce_scores_kernel<<<grid, 128, 0, st>>>(a); p4v_count_launch();
+  const int tasks = a.n_cand * (a.mode == P4V_SG_COLUMN ? a.tiles_n : a.n_keys);
+  reduce_scores_kernel<<<p4v_cdiv(tasks, 8), 256, 0, st>>>(a); p4v_count_launch();
   P4V_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
-int p4v_finish_step(const FinishArgs& a, cudaStream_t st) {
-  const long long total = a.nseg > 0 ? (long long)a.P * a.tiles * P4V_TILE * a.commit_chunks : 0;
-  const int grid = grid_for(total, 256, 148 * 8);
-  finish_step_kernel<<<grid, 256, (size_t)a.n_groups * sizeof(int), st>>>(a, a.commit_chunks); p4v_count_launch();
+int p4v_select_step(const SelectArgs& a, cudaStream_t st) {
+  int threads = 32 * a.n_groups;
+  if (a.has_next || threads > 1024) threads = 1024;
+  if (threads < 32) threads = 32;
+  select_step_kernel<<<1, threads, 0, st>>>(a); p4v_count_launch();
+  P4V_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int p4v_commit_step(const CommitArgs& a, cudaStream_t st) {
+  if (a.nseg <= 0) return 0;
+  const long long total = (long long)a.P * a.tiles * P4V_TILE * a.commit_chunks;
+  commit_step_kernel<<<grid_for(total, 256, 148 * 8), 256, 0, st>>>(a, a.commit_chunks); p4v_count_launch();
   P4V_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -60,27 +60,35 @@ int p4v_step_tables(const StepTablesArgs& a, cudaStream_t st);
 struct ReduceArgs {
   const float* partial; int n_cand;
   int P, tiles_m, tiles_n, order;
-  int mode;                  // P4V_SG_COLUMN: group = global16colgroup / cg_per_group ; P4V_SG_PROBLEM: group = p % n_groups
-  int n_groups, cg_per_group;
-  double inv_count;          // 1 / (tokens * features) normalisation of the reference's means
-  const float* gscale;
-  double* scores;            // [n_cand][n_groups]
+  int mode;                  // P4V_SG_COLUMN: key = global 16-column group (tn*8+i) ; P4V_SG_PROBLEM: key = p % n_keys
+  int n_keys;
+  double* sums;              // [n_cand][n_keys]  fixed-order fp64 sums of the sweep partials
 };
 int p4v_reduce_scores(const ReduceArgs& a, cudaStream_t st);
 
-struct CommitSeg { int src_off, dst_off, kb; };
-struct FinishArgs {
-  const double* scores; int n_cand, n_groups;
+// One block: scores[c][g] = -norm * sum_{k in group g} sums[c][k]; argmax over c per group (first maximum, NaN wins,
+// like torch.argmax); publishes the new step sizes, the score log and -- when has_next -- the scale tables of the
+// next search step (which depend on the step sizes just chosen).
+struct SelectArgs {
+  const double* sums; int n_cand, n_keys, n_groups, keys_per_group;
+  double inv_count; const float* gscale;
   const float* factors;
   const float* d0; float* d; int d_stride, d_col;    // d[g * d_stride + d_col] = fl(f[best_g] * d0[...])
-  int* best;                                         // [n_groups] (optional)
+  int* best;                                         // [n_groups]
   float* score_log;                                  // [n_cand][n_groups] fp32 (optional)
-  // image commit: rows of group g = [g*rows_per_group, (g+1)*rows_per_group) ; rows_per_group==0 -> all rows group 0
-  // ; problem mode: group = p % n_groups
+  int has_next; StepTablesArgs next;
+};
+int p4v_select_step(const SelectArgs& a, cudaStream_t st);
+
+// Copy the winning candidate's image slabs into the current image.
+struct CommitSeg { int src_off, dst_off, kb; };
+struct CommitArgs {
+  const int* best; int n_groups;
+  // rows of group g = [g*rows_per_group, (g+1)*rows_per_group) ; rows_per_group==0 -> all rows group 0 ; problem mode: group = p % n_groups
   const uint8_t* cand; unsigned long long cand_plane_stride, cand_tile_bytes;
   uint8_t* cur; unsigned long long cur_tile_bytes;
-  int P, rows, tiles, rows_per_group, problem_groups;
+  int P, tiles, rows_per_group, problem_groups;
   const CommitSeg* segs; int nseg;
   int commit_chunks;                                 // sum over segs of kb/16
 };
-int p4v_finish_step(const FinishArgs& a, cudaStream_t st);
+int p4v_commit_step(const CommitArgs& a, cudaStream_t st);

@@ -5,42 +5,44 @@
 // (quant_layers/linear.py:466-488, :507-526; quant_layers/matmul.py:500-514, :541-555)
 // without ever writing a candidate output to HBM.
 //
-// One persistent CTA per SM.  Work = (output tile 128x128) x (candidate range),
-// split stream-K style over the CTAs.  Per tile fragment:
-//   1. the 256 epilogue threads load r = y - bias and g = grad * 2^k for their
-//      (row, 64 columns) into REGISTERS -- they stay there for all candidates;
-//   2. "fixed" segments (everything that does not change with the candidate) are
-//      multiplied on the tensor cores and subtracted: r -= scale * acc;
-//   3. per candidate only the segment(s) touched by the candidate step size are
-//      multiplied (TMA bulk copy -> smem ring -> tcgen05.mma -> TMEM), and the
-//      epilogue forms (g * (r - scale_c * acc))^2 straight from TMEM, reduces it over
-//      the 32 rows of the warp with shuffles and writes one partial per 16 columns.
+// One persistent CTA per SM.  Work = (output tile 128x128) x (candidates).  Whole tiles are dealt
+// round-robin in waves of gridDim.x (CTAs that run together share operand tiles in L2); the last partial
+// wave is split at candidate granularity so that every SM finishes together.  Per tile fragment:
+//   1. the 256 epilogue threads load r = y - bias and g = grad * 2^k for their (row, 64 columns) into
+//      REGISTERS -- they stay there for all candidates;
+//   2. "fixed" segments (everything the candidate does not change) are multiplied on the tensor cores and
+//      subtracted: r -= scale * acc;
+//   3. per candidate only the segment(s) touched by the candidate step size are multiplied (TMA bulk copy
+//      -> smem ring -> tcgen05.mma -> TMEM); the epilogue forms (g * (r - scale_c * acc))^2 straight from
+//      TMEM, reduces it over the 32 rows of a warp with shuffles and writes one partial per 16 columns.
 // Roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 4..11 = epilogue
 // (setmaxnreg moves the register budget of warpgroup 0 to the epilogue warpgroups).
 #include "common.cuh"
+#include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
 namespace {
 
-constexpr int kStages = 4;
-constexpr int kStageBytes = P4V_TILE * P4V_JOB_KB;       // 16 KB per operand
-constexpr int kAccSlots = 3;
+constexpr int kMaxStages = 16;
 constexpr int kAccCols = 128;
 constexpr int kTmemCols = 512;
 constexpr int kEpiThreads = 256;
+constexpr int kEpiWarps = 8;
 constexpr int kThreads = 128 + kEpiThreads;   // warpgroup 0: producer, MMA, 2 idle warps; warpgroups 1-2: epilogue
+constexpr int kSmemBudget = 200 * 1024;       // ring + resident operand
 
-struct SmemLayout {
-  alignas(128) uint8_t stageR[kStages][kStageBytes];
-  alignas(128) uint8_t stageC[kStages][kStageBytes];
+struct SmemCtl {
   alignas(16) P4VJob jobs[P4V_MAX_JOBS];
   float fixs[P4V_MAX_GROUPS][P4V_TILE_CG];
   float candA[P4V_MAX_CAND][P4V_TILE_CG];
   float candB[P4V_MAX_GROUPS][P4V_TILE_CG];
-  alignas(8) unsigned long long full[kStages];
-  unsigned long long empty[kStages];
-  unsigned long long acc_full[kAccSlots];
-  unsigned long long acc_empty[kAccSlots];
+  alignas(8) unsigned long long full[kMaxStages];
+  unsigned long long empty[kMaxStages];
+  unsigned long long acc_full[4];
+  unsigned long long acc_empty[4];
+  unsigned long long res_full[2];
+  unsigned long long res_empty[2];
   uint32_t tmem_base;
 };
 
@@ -77,9 +79,9 @@ __device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
   while (!mbar_try(addr, parity))
     if (clock64() - t0 > 4000000000ll) mbar_timeout(addr, parity);
 }
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, void* bar) {
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, void* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -120,6 +122,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld32f(uint32_t taddr, float* v) {   // same, straight into a float register array
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]),
+        "=f"(v[8]), "=f"(v[9]), "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15]),
+        "=f"(v[16]), "=f"(v[17]), "=f"(v[18]), "=f"(v[19]), "=f"(v[20]), "=f"(v[21]), "=f"(v[22]), "=f"(v[23]),
+        "=f"(v[24]), "=f"(v[25]), "=f"(v[26]), "=f"(v[27]), "=f"(v[28]), "=f"(v[29]), "=f"(v[30]), "=f"(v[31])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -135,20 +148,37 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// ---- work distribution -------------------------------------------------------------------------
 struct Frag { int tile, p, tm, tn, c0, c1; };
-
-__device__ __forceinline__ bool next_frag(const SweepParams& P, long long& u, long long u_end, Frag& f) {
-  if (u >= u_end) return false;
-  f.tile = (int)(u / P.n_cand);
-  f.c0 = (int)(u % P.n_cand);
-  long long rem = u_end - u;
-  f.c1 = (int)((rem < (long long)(P.n_cand - f.c0)) ? f.c0 + rem : P.n_cand);
-  int per_p = P.tiles_m * P.tiles_n;
+struct Sched {
+  int waves, k;                 // whole-tile waves, next wave index
+  long long u, u_end;           // candidate-granular units of the tail wave
+  int tail_tile0;
+};
+__device__ __forceinline__ void sched_init(const SweepParams& P, Sched& s) {
+  const int tiles = P.P * P.tiles_m * P.tiles_n;
+  const int G = gridDim.x;
+  s.waves = tiles / G; s.k = 0;
+  const long long tail_units = (long long)(tiles % G) * P.n_cand;
+  s.u = tail_units * blockIdx.x / G; s.u_end = tail_units * (blockIdx.x + 1) / G;
+  s.tail_tile0 = s.waves * G;
+}
+__device__ __forceinline__ bool next_frag(const SweepParams& P, Sched& s, Frag& f) {
+  if (s.k < s.waves) {
+    f.tile = s.k * gridDim.x + blockIdx.x; f.c0 = 0; f.c1 = P.n_cand; ++s.k;
+  } else {
+    if (s.u >= s.u_end) return false;
+    f.tile = s.tail_tile0 + (int)(s.u / P.n_cand);
+    f.c0 = (int)(s.u % P.n_cand);
+    const long long rem = s.u_end - s.u;
+    f.c1 = (int)((rem < (long long)(P.n_cand - f.c0)) ? f.c0 + rem : P.n_cand);
+    s.u += f.c1 - f.c0;
+  }
+  const int per_p = P.tiles_m * P.tiles_n;
   f.p = f.tile / per_p;
-  int t = f.tile % per_p;
+  const int t = f.tile % per_p;
   if (P.order == 0) { f.tm = t % P.tiles_m; f.tn = t / P.tiles_m; }
   else              { f.tn = t % P.tiles_n; f.tm = t / P.tiles_n; }
-  u += f.c1 - f.c0;
   return true;
 }
 
@@ -158,36 +188,146 @@ __device__ __forceinline__ float acc_to_float(uint32_t a) {
   else return __uint_as_float(a);
 }
 
-// Reduce 4 per-lane partial sums over the 32 lanes (= 32 rows).  After the call lane
-// 8*k (k=0..3) holds the total of value k.  Fixed order => deterministic.
+// ---- packed fp32x2 math (sm_100: FFMA2/FMUL2 halve the issue slots of the epilogue) ----
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
+// Half an accumulator (32 of this thread's 64 columns, already in registers) against the running residual.
+//   kScore == false:  r -= s * acc                        (fixed segments / non-final candidate segments)
+//   kScore == true :  p = sum (g * (r - s*acc))^2 per 16 columns   (final candidate segment; r is not modified)
+template <bool kInt8, bool kScore, bool kPacked, int OFF>
+__device__ __forceinline__ void consume_chunk(const uint32_t (&a)[32], float (&r)[64], const float (&g)[64],
+                                              const float s_lo, const float s_hi, float& p_lo, float& p_hi) {
+  if constexpr (kPacked) {
+    f32x2 q_lo = 0ull, q_hi = 0ull;
+    const f32x2 ns_lo = pack2(-s_lo, -s_lo), ns_hi = pack2(-s_hi, -s_hi);
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      const f32x2 f = pack2(acc_to_float<kInt8>(a[j]), acc_to_float<kInt8>(a[j + 1]));
+      const f32x2 d = fma2(j < 16 ? ns_lo : ns_hi, f, pack2(r[OFF + j], r[OFF + j + 1]));
+      if constexpr (kScore) {
+        const f32x2 w = mul2(pack2(g[OFF + j], g[OFF + j + 1]), d);
+        if (j < 16) q_lo = fma2(w, w, q_lo); else q_hi = fma2(w, w, q_hi);
+      } else {
+        unpack2(d, r[OFF + j], r[OFF + j + 1]);
+      }
+    }
+    if constexpr (kScore) { float x, y; unpack2(q_lo, x, y); p_lo = x + y; unpack2(q_hi, x, y); p_hi = x + y; }
+  } else {
+    float q_lo = 0.f, q_hi = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float d = fmaf(-(j < 16 ? s_lo : s_hi), acc_to_float<kInt8>(a[j]), r[OFF + j]);
+      if constexpr (kScore) { const float w = g[OFF + j] * d; if (j < 16) q_lo = fmaf(w, w, q_lo); else q_hi = fmaf(w, w, q_hi); }
+      else r[OFF + j] = d;
+    }
+    if constexpr (kScore) { p_lo = q_lo; p_hi = q_hi; }
+  }
+}
+
+// Reduce 16 per-lane values (4 candidates x 4 column groups) over the 32 lanes (= rows) of the warp.
+// Afterwards lane L holds the total of value 8*b4 + 4*b3 + 2*b2 + b1 (bk = bit k of L).  Fixed order.
+__device__ __forceinline__ float reduce16_over_rows(float (&v)[16], int lane) {
+  const unsigned full = 0xffffffffu;
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+  float w8[8], w4[4], w2[2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { const float send = b4 ? v[i] : v[8 + i]; const float keep = b4 ? v[8 + i] : v[i]; w8[i] = keep + __shfl_xor_sync(full, send, 16); }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float send = b3 ? w8[i] : w8[4 + i]; const float keep = b3 ? w8[4 + i] : w8[i]; w4[i] = keep + __shfl_xor_sync(full, send, 8); }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) { const float send = b2 ? w4[i] : w4[2 + i]; const float keep = b2 ? w4[2 + i] : w4[i]; w2[i] = keep + __shfl_xor_sync(full, send, 4); }
+  const float send = b1 ? w2[0] : w2[1]; float k = (b1 ? w2[1] : w2[0]) + __shfl_xor_sync(full, send, 2);
+  k += __shfl_xor_sync(full, k, 1);
+  return k;
+}
+// Same for 8 values (2 candidates x 4 groups): lane L holds value 4*b4 + 2*b3 + b2.
+__device__ __forceinline__ float reduce8_over_rows(float (&v)[8], int lane) {
+  const unsigned full = 0xffffffffu;
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+  float w4[4], w2[2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float send = b4 ? v[i] : v[4 + i]; const float keep = b4 ? v[4 + i] : v[i]; w4[i] = keep + __shfl_xor_sync(full, send, 16); }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) { const float send = b3 ? w4[i] : w4[2 + i]; const float keep = b3 ? w4[2 + i] : w4[i]; w2[i] = keep + __shfl_xor_sync(full, send, 8); }
+  const float send = b2 ? w2[0] : w2[1]; float k = (b2 ? w2[1] : w2[0]) + __shfl_xor_sync(full, send, 4);
+  k += __shfl_xor_sync(full, k, 2);
+  k += __shfl_xor_sync(full, k, 1);
+  return k;
+}
+// Same for 4 values: lane 8*k holds value k.
 __device__ __forceinline__ float reduce4_over_rows(float v0, float v1, float v2, float v3, int lane) {
   const unsigned full = 0xffffffffu;
-  bool hi16 = lane & 16;
-  float s0 = hi16 ? v0 : v2, s1 = hi16 ? v1 : v3;      // what this lane sends away
-  float k0 = hi16 ? v2 : v0, k1 = hi16 ? v3 : v1;      // what it keeps
+  const bool hi16 = lane & 16;
+  float s0 = hi16 ? v0 : v2, s1 = hi16 ? v1 : v3;
+  float k0 = hi16 ? v2 : v0, k1 = hi16 ? v3 : v1;
   k0 += __shfl_xor_sync(full, s0, 16);
   k1 += __shfl_xor_sync(full, s1, 16);
-  bool hi8 = lane & 8;
+  const bool hi8 = lane & 8;
   float s = hi8 ? k0 : k1, k = hi8 ? k1 : k0;
   k += __shfl_xor_sync(full, s, 8);
   k += __shfl_xor_sync(full, k, 4);
   k += __shfl_xor_sync(full, k, 2);
   k += __shfl_xor_sync(full, k, 1);
-  return k;   // lanes with (bit4,bit3) = (a,b) hold value 2a+b
+  return k;
 }
 
-template <bool kInt8, bool kSingle>
+// ---- epilogue accumulator pipeline ----------------------------------------------------------------
+// The epilogue walks the accumulators of the TMEM ring in order.  `a0` always holds the first 32 columns
+// of the accumulator about to be consumed (already complete); while the CUDA cores work on one half the
+// TMEM load of the next half is in flight, and the slot goes back to the MMA warp as soon as its second
+// half has landed in registers.
+struct AccRing { uint32_t slot, phase, nslots; };
+
+__device__ __forceinline__ void acc_begin(SmemCtl& S, AccRing& ring, uint32_t tbase, uint32_t (&a0)[32]) {
+  mbar_wait(&S.acc_full[ring.slot], ring.phase);
+  tc_fence_after();
+  tmem_ld32(tbase + ring.slot * kAccCols, a0);
+  tmem_wait_ld();
+}
+
+template <bool kInt8, bool kScore, bool kPacked>
+__device__ __forceinline__ void acc_step(SmemCtl& S, AccRing& ring, uint32_t tbase, int lane, uint32_t (&a0)[32],
+                                         uint32_t (&a1)[32], float (&r)[64], const float (&g)[64], const float4 sc,
+                                         float (&p)[4], const bool has_next) {
+  tmem_ld32(tbase + ring.slot * kAccCols + 32, a1);
+  consume_chunk<kInt8, kScore, kPacked, 0>(a0, r, g, sc.x, sc.y, p[0], p[1]);
+  tmem_wait_ld();
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(&S.acc_empty[ring.slot]);      // one arrival per epilogue warp
+  if (++ring.slot == ring.nslots) { ring.slot = 0; ring.phase ^= 1; }
+  if (has_next) {
+    mbar_wait(&S.acc_full[ring.slot], ring.phase);
+    tc_fence_after();
+    tmem_ld32(tbase + ring.slot * kAccCols, a0);
+  }
+  consume_chunk<kInt8, kScore, kPacked, 32>(a1, r, g, sc.z, sc.w, p[2], p[3]);
+  if (has_next) tmem_wait_ld();
+}
+
+template <bool kInt8, bool kSingle, bool kPacked>
 __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_constant__ SweepParams P) {
   extern __shared__ uint8_t smem_raw[];
-  SmemLayout& S = *reinterpret_cast<SmemLayout*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  // carve: [ring R stages][ring C stages][resident R x2][control]
+  const uint32_t sR = P.stage_r_bytes, sC = P.stage_c_bytes, nst = P.n_stages, resB = P.resident_bytes;
+  const uint32_t ringR = smem_u32(smem), ringC = ringR + nst * sR, resR = ringC + nst * sC;
+  SmemCtl& S = *reinterpret_cast<SmemCtl*>(smem + (size_t)nst * (sR + sC) + 2 * (size_t)resB);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t kSlots = kSingle ? 4 : 3;            // single-segment steps do not park the target in TMEM
+  constexpr uint32_t kAccBase = kSingle ? 0 : kAccCols;
 
   // ---- one-time setup ----
   const int n_jobs = P.n_fixed_jobs + P.n_cand_jobs;
   for (int i = threadIdx.x; i < n_jobs; i += kThreads) S.jobs[i] = P.jobs[i];
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(&S.full[i], 1); mbar_init(&S.empty[i], 1); }
-    for (int i = 0; i < kAccSlots; ++i) { mbar_init(&S.acc_full[i], 1); mbar_init(&S.acc_empty[i], kEpiThreads); }
+    for (uint32_t i = 0; i < nst; ++i) { mbar_init(&S.full[i], 1); mbar_init(&S.empty[i], 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&S.acc_full[i], 1); mbar_init(&S.acc_empty[i], kEpiWarps); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&S.res_full[i], 1); mbar_init(&S.res_empty[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -199,9 +339,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
   tc_fence_after();
   const uint32_t tmem = S.tmem_base;
 
-  const long long units = (long long)P.P * P.tiles_m * P.tiles_n * P.n_cand;
-  long long u = units * blockIdx.x / gridDim.x;
-  const long long u_end = units * (blockIdx.x + 1) / gridDim.x;
+  Sched sched; sched_init(P, sched);
   Frag f;
 
   if (warp < 4) {
@@ -209,21 +347,37 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
   if (warp == 0) {
     // ======================= TMA producer =======================
     if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
+      uint32_t stage = 0, phase = 0, rbuf = 0, rphase = 0;
       auto issue = [&](const P4VJob& j, const Frag& fr, int c) {
         mbar_wait(&S.empty[stage], phase ^ 1);
         const uint32_t bytes = (uint32_t)j.kb * P4V_TILE;
         const size_t rt = (size_t)(fr.p * P.tiles_m + fr.tm), ct = (size_t)(fr.p * P.tiles_n + fr.tn);
-        const uint8_t* r = ((j.flags & P4V_JOB_RCAND) ? P.R_cand + (size_t)c * P.R_cand_stride + rt * P.R_cand_tile_bytes
-                                                      : P.R_cur + rt * P.R_tile_bytes) + j.r_off;
         const uint8_t* cc = ((j.flags & P4V_JOB_CCAND) ? P.C_cand + (size_t)c * P.C_cand_stride + ct * P.C_cand_tile_bytes
                                                        : P.C_cur + ct * P.C_tile_bytes) + j.c_off;
-        mbar_expect_tx(&S.full[stage], 2 * bytes);
-        bulk_g2s(S.stageR[stage], r, bytes, &S.full[stage]);
-        bulk_g2s(S.stageC[stage], cc, bytes, &S.full[stage]);
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        if (j.flags & P4V_JOB_RRES) {
+          mbar_expect_tx(&S.full[stage], bytes);
+        } else {
+          const uint8_t* r = ((j.flags & P4V_JOB_RCAND) ? P.R_cand + (size_t)c * P.R_cand_stride + rt * P.R_cand_tile_bytes
+                                                        : P.R_cur + rt * P.R_tile_bytes) + j.r_off;
+          mbar_expect_tx(&S.full[stage], 2 * bytes);
+          bulk_g2s(ringR + stage * sR, r, bytes, &S.full[stage]);
+        }
+        bulk_g2s(ringC + stage * sC, cc, bytes, &S.full[stage]);
+        if (++stage == nst) { stage = 0; phase ^= 1; }
       };
-      while (next_frag(P, u, u_end, f)) {
+      while (next_frag(P, sched, f)) {
+        if (resB) {      // row operand of the candidate jobs: once per fragment, reused by every candidate
+          mbar_wait(&S.res_empty[rbuf], rphase ^ 1);
+          uint32_t total = 0;
+          for (int j = 0; j < P.n_cand_jobs; ++j) total += (uint32_t)S.jobs[P.n_fixed_jobs + j].kb * P4V_TILE;
+          mbar_expect_tx(&S.res_full[rbuf], total);
+          const uint8_t* rbase = P.R_cur + (size_t)(f.p * P.tiles_m + f.tm) * P.R_tile_bytes;
+          for (int j = 0; j < P.n_cand_jobs; ++j) {
+            const P4VJob& jb = S.jobs[P.n_fixed_jobs + j];
+            bulk_g2s(resR + rbuf * resB + jb.res_off, rbase + jb.r_off, (uint32_t)jb.kb * P4V_TILE, &S.res_full[rbuf]);
+          }
+          if (++rbuf == 2) { rbuf = 0; rphase ^= 1; }
+        }
         for (int j = 0; j < P.n_fixed_jobs; ++j) issue(S.jobs[j], f, 0);
         for (int c = f.c0; c < f.c1; ++c)
           for (int j = 0; j < P.n_cand_jobs; ++j) issue(S.jobs[P.n_fixed_jobs + j], f, c);
@@ -233,16 +387,17 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
   } else if (warp == 1) {
     // ======================= MMA issuer =======================
     if (lane == 0) {
-      uint32_t stage = 0, phase = 0, slot = 0, slot_phase = 0;
-      auto run = [&](const P4VJob& j) {
+      uint32_t stage = 0, phase = 0, slot = 0, slot_phase = 0, rbuf = 0, rphase = 0;
+      auto run = [&](const P4VJob& j, uint32_t res_base) {
         if (j.flags & P4V_JOB_FIRST) {
           mbar_wait(&S.acc_empty[slot], slot_phase ^ 1);
           tc_fence_after();
         }
         mbar_wait(&S.full[stage], phase);
         tc_fence_after();
-        const uint32_t ra = smem_u32(S.stageR[stage]), ca = smem_u32(S.stageC[stage]);
-        const uint32_t d = tmem + kAccCols + slot * kAccCols;
+        const uint32_t ra = (j.flags & P4V_JOB_RRES) ? res_base + j.res_off : ringR + stage * sR;
+        const uint32_t ca = ringC + stage * sC;
+        const uint32_t d = tmem + kAccBase + slot * kAccCols;
         const int ksteps = j.kb >> 5;
         for (int k = 0; k < ksteps; ++k) {
           uint32_t acc = ((j.flags & P4V_JOB_FIRST) && k == 0) ? 0u : 1u;
@@ -251,14 +406,24 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
         tc_commit(&S.empty[stage]);
         if (j.flags & P4V_JOB_LAST) {
           tc_commit(&S.acc_full[slot]);
-          if (++slot == kAccSlots) { slot = 0; slot_phase ^= 1; }
+          if (++slot == kSlots) { slot = 0; slot_phase ^= 1; }
         }
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        if (++stage == nst) { stage = 0; phase ^= 1; }
       };
-      while (next_frag(P, u, u_end, f)) {
-        for (int j = 0; j < P.n_fixed_jobs; ++j) run(S.jobs[j]);
+      while (next_frag(P, sched, f)) {
+        for (int j = 0; j < P.n_fixed_jobs; ++j) run(S.jobs[j], 0);
+        uint32_t res_base = 0;
+        if (resB) {
+          mbar_wait(&S.res_full[rbuf], rphase);
+          tc_fence_after();
+          res_base = resR + rbuf * resB;
+        }
         for (int c = f.c0; c < f.c1; ++c)
-          for (int j = 0; j < P.n_cand_jobs; ++j) run(S.jobs[P.n_fixed_jobs + j]);
+          for (int j = 0; j < P.n_cand_jobs; ++j) run(S.jobs[P.n_fixed_jobs + j], res_base);
+        if (resB) {
+          tc_commit(&S.res_empty[rbuf]);           // resident buffer free once every MMA reading it has retired
+          if (++rbuf == 2) { rbuf = 0; rphase ^= 1; }
+        }
       }
     }
     __syncwarp();
@@ -271,11 +436,14 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
     const int hf = ew >> 2;                  // column half
     const int et = threadIdx.x - 128;        // 0..255
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const uint32_t tbase = tmem + lane_addr + kAccBase + hf * 64;       // this thread's columns of slot 0
+    const uint32_t tstore = tmem + lane_addr + hf * 64;                 // parked residual target (!kSingle)
     const float gs = P.out ? 1.f : *P.gscale;
-    uint32_t slot = 0, slot_phase = 0;
+    AccRing ring{0u, 0u, kSlots};
     float r[64], g[64];
+    uint32_t a0[32], a1[32];
 
-    while (next_frag(P, u, u_end, f)) {
+    while (next_frag(P, sched, f)) {
       // -- scale tables for this tile's 8 column groups --
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads));   // previous fragment done with the tables
       {
@@ -324,24 +492,13 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads));   // tables visible
 
       // -- fixed segments: r -= scale * acc --
-      for (int gi = 0; gi < P.n_fixed_groups; ++gi) {
-        mbar_wait(&S.acc_full[slot], slot_phase);
-        tc_fence_after();
-        const uint32_t taddr = tmem + lane_addr + kAccCols + slot * kAccCols + hf * 64;
-        const float4 sc = *reinterpret_cast<const float4*>(&S.fixs[gi][hf * 4]);
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-          uint32_t a[32];
-          tmem_ld32(taddr + ch * 32, a);
-          tmem_wait_ld();
-          const float s_lo = ch ? sc.z : sc.x, s_hi = ch ? sc.w : sc.y;
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            r[ch * 32 + j] = fmaf(-(j < 16 ? s_lo : s_hi), acc_to_float<kInt8>(a[j]), r[ch * 32 + j]);
+      float pdummy[4];
+      if (P.n_fixed_groups > 0) {
+        acc_begin(S, ring, tbase, a0);
+        for (int gi = 0; gi < P.n_fixed_groups; ++gi) {
+          const float4 sc = *reinterpret_cast<const float4*>(&S.fixs[gi][hf * 4]);
+          acc_step<kInt8, false, kPacked>(S, ring, tbase, lane, a0, a1, r, g, sc, pdummy, gi + 1 < P.n_fixed_groups);
         }
-        tc_fence_before();
-        mbar_arrive(&S.acc_empty[slot]);
-        if (++slot == kAccSlots) { slot = 0; slot_phase ^= 1; }
       }
       if (P.out != nullptr) {
         const int gm = f.tm * P4V_TILE + quarter * 32 + lane;
@@ -353,63 +510,53 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
         }
         continue;
       }
-      if constexpr (!kSingle) {   // park the residual target in TMEM columns [0,128)
-        tmem_st32(tmem + lane_addr + hf * 64, r);
-        tmem_st32(tmem + lane_addr + hf * 64 + 32, r + 32);
-        tmem_wait_st();
-      }
-
-      // -- candidates --
       float* part_base = P.partial + ((size_t)f.tile * P.n_cand) * 32 + quarter * 8 + hf * 4;
-      for (int c = f.c0; c < f.c1; ++c) {
-        const float4 ca = *reinterpret_cast<const float4*>(&S.candA[c][hf * 4]);
-        float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
-        if constexpr (!kSingle) {
-          uint32_t t[32];
-          tmem_ld32(tmem + lane_addr + hf * 64, t);
-          tmem_wait_ld();
+
+      if constexpr (kSingle) {
+        // -- one accumulator per candidate; two candidates per cross-row reduction --
+        if (f.c1 > f.c0) acc_begin(S, ring, tbase, a0);
+        for (int cb0 = f.c0; cb0 < f.c1; cb0 += 2) {
+          float v[8];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = __uint_as_float(t[j]);
-          tmem_ld32(tmem + lane_addr + hf * 64 + 32, t);
-          tmem_wait_ld();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) r[32 + j] = __uint_as_float(t[j]);
-        }
-        for (int gi = 0; gi < P.n_cand_groups; ++gi) {
-          mbar_wait(&S.acc_full[slot], slot_phase);
-          tc_fence_after();
-          const uint32_t taddr = tmem + lane_addr + kAccCols + slot * kAccCols + hf * 64;
-          const float4 cb = *reinterpret_cast<const float4*>(&S.candB[gi][hf * 4]);
-          const bool noA = (P.cand_noA_mask >> gi) & 1ull;
-          const float4 sc = noA ? cb : make_float4(ca.x * cb.x, ca.y * cb.y, ca.z * cb.z, ca.w * cb.w);
-          const bool last = kSingle || (gi == P.n_cand_groups - 1);
-#pragma unroll
-          for (int ch = 0; ch < 2; ++ch) {
-            uint32_t a[32];
-            tmem_ld32(taddr + ch * 32, a);
-            tmem_wait_ld();
-            const float s_lo = ch ? sc.z : sc.x, s_hi = ch ? sc.w : sc.y;
-            if (last) {
-              float q_lo = 0.f, q_hi = 0.f;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float d = fmaf(-(j < 16 ? s_lo : s_hi), acc_to_float<kInt8>(a[j]), r[ch * 32 + j]);
-                const float w = g[ch * 32 + j] * d;
-                if (j < 16) q_lo = fmaf(w, w, q_lo); else q_hi = fmaf(w, w, q_hi);
-              }
-              if (ch == 0) { p0 = q_lo; p1 = q_hi; } else { p2 = q_lo; p3 = q_hi; }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                r[ch * 32 + j] = fmaf(-(j < 16 ? s_lo : s_hi), acc_to_float<kInt8>(a[j]), r[ch * 32 + j]);
+          for (int ci = 0; ci < 2; ++ci) {
+            float p[4] = {0.f, 0.f, 0.f, 0.f};
+            const int c = cb0 + ci;
+            if (c < f.c1) {
+              const float4 ca = *reinterpret_cast<const float4*>(&S.candA[c][hf * 4]);
+              const float4 cb = *reinterpret_cast<const float4*>(&S.candB[0][hf * 4]);
+              const bool noA = P.cand_noA_mask & 1ull;
+              const float4 sc = noA ? cb : make_float4(ca.x * cb.x, ca.y * cb.y, ca.z * cb.z, ca.w * cb.w);
+              acc_step<kInt8, true, kPacked>(S, ring, tbase, lane, a0, a1, r, g, sc, p, c + 1 < f.c1);
             }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[ci * 4 + i] = p[i];
           }
-          tc_fence_before();
-          mbar_arrive(&S.acc_empty[slot]);
-          if (++slot == kAccSlots) { slot = 0; slot_phase ^= 1; }
+          const float tot = reduce8_over_rows(v, lane);
+          const int ci = (lane >> 4) & 1, gi4 = ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+          if (!(lane & 3) && cb0 + ci < f.c1) part_base[(size_t)(cb0 + ci) * 32 + gi4] = tot;
         }
-        const float tot = reduce4_over_rows(p0, p1, p2, p3, lane);
-        if ((lane & 7) == 0) part_base[(size_t)c * 32 + (lane >> 3)] = tot;
+      } else {
+        // -- several segments per candidate: park the residual target in TMEM columns [0,128) --
+        tmem_st32(tstore, r);
+        tmem_st32(tstore + 32, r + 32);
+        tmem_wait_st();
+        for (int c = f.c0; c < f.c1; ++c) {
+          const float4 ca = *reinterpret_cast<const float4*>(&S.candA[c][hf * 4]);
+          float p[4] = {0.f, 0.f, 0.f, 0.f};
+          tmem_ld32f(tstore, r);
+          tmem_ld32f(tstore + 32, r + 32);
+          tmem_wait_ld();
+          acc_begin(S, ring, tbase, a0);
+          for (int gi = 0; gi < P.n_cand_groups; ++gi) {
+            const float4 cb = *reinterpret_cast<const float4*>(&S.candB[gi][hf * 4]);
+            const bool noA = (P.cand_noA_mask >> gi) & 1ull;
+            const float4 sc = noA ? cb : make_float4(ca.x * cb.x, ca.y * cb.y, ca.z * cb.z, ca.w * cb.w);
+            if (gi == P.n_cand_groups - 1) acc_step<kInt8, true, kPacked>(S, ring, tbase, lane, a0, a1, r, g, sc, p, false);
+            else acc_step<kInt8, false, kPacked>(S, ring, tbase, lane, a0, a1, r, g, sc, p, true);
+          }
+          const float tot = reduce4_over_rows(p[0], p[1], p[2], p[3], lane);
+          if ((lane & 7) == 0) part_base[(size_t)c * 32 + (lane >> 3)] = tot;
+        }
       }
     }
   }
@@ -425,23 +572,45 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
 
 }  // namespace
 
-int p4v_launch_sweep_tc(const SweepParams& p, int num_sms, cudaStream_t st) {
-  P4V_REQUIRE(p.n_fixed_jobs + p.n_cand_jobs <= P4V_MAX_JOBS, "sweep: too many jobs (%d)", p.n_fixed_jobs + p.n_cand_jobs);
+int p4v_launch_sweep_tc(const SweepParams& p_in, const P4VJob* host_jobs, int num_sms, cudaStream_t st) {
+  SweepParams p = p_in;
+  const int n_jobs = p.n_fixed_jobs + p.n_cand_jobs;
+  P4V_REQUIRE(n_jobs <= P4V_MAX_JOBS, "sweep: too many jobs (%d)", n_jobs);
   P4V_REQUIRE(p.n_fixed_groups <= P4V_MAX_GROUPS && p.n_cand_groups <= P4V_MAX_GROUPS, "sweep: too many segment groups");
   P4V_REQUIRE(p.n_cand <= P4V_MAX_CAND && p.n_cand >= 1, "sweep: bad candidate count");
   P4V_REQUIRE(p.out != nullptr ? (p.n_cand == 1 && p.n_cand_jobs == 0) : p.n_cand_groups >= 1, "sweep: bad mode");
-  const long long units = (long long)p.P * p.tiles_m * p.tiles_n * p.n_cand;
+  const long long tiles = (long long)p.P * p.tiles_m * p.tiles_n;
+  const long long units = tiles * p.n_cand;
   int grid = (int)(units < num_sms ? units : num_sms);
   if (grid < 1) return 0;
-  const size_t smem = sizeof(SmemLayout) + 128;
-  const bool single = p.n_cand_groups == 1;
-#define P4V_LAUNCH(I8, SG)                                                                             \
+  // smem plan: stage size = largest job; resident row operand when the host marked the candidate jobs P4V_JOB_RRES
+  uint32_t max_kb = 32, res_bytes = 0;
+  bool any_r_stream = false;
+  for (int j = 0; j < n_jobs; ++j) {
+    if (host_jobs[j].kb > max_kb) max_kb = host_jobs[j].kb;
+    if (host_jobs[j].flags & P4V_JOB_RRES) res_bytes = std::max(res_bytes, host_jobs[j].res_off + (uint32_t)host_jobs[j].kb * P4V_TILE);
+    else any_r_stream = true;
+  }
+  p.stage_r_bytes = any_r_stream ? max_kb * P4V_TILE : 0;
+  p.stage_c_bytes = max_kb * P4V_TILE;
+  p.resident_bytes = res_bytes;
+  const uint32_t per_stage = p.stage_r_bytes + p.stage_c_bytes;
+  int nst = (int)((kSmemBudget - 2 * (long long)res_bytes) / per_stage);
+  if (nst > kMaxStages) nst = kMaxStages;
+  P4V_REQUIRE(nst >= 2, "sweep: operand tiles do not fit the shared-memory ring");
+  p.n_stages = nst;
+  const size_t smem = (size_t)nst * per_stage + 2 * (size_t)res_bytes + sizeof(SmemCtl) + 256;
+  const bool single = p.n_cand_groups == 1 && p.out == nullptr;
+#define P4V_LAUNCH(I8, SG, PK)                                                                         \
   do {                                                                                                 \
-    P4V_CUDA_OK(cudaFuncSetAttribute(sweep_tc_kernel<I8, SG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    sweep_tc_kernel<I8, SG><<<grid, kThreads, smem, st>>>(p);                                          \
+    P4V_CUDA_OK(cudaFuncSetAttribute(sweep_tc_kernel<I8, SG, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    sweep_tc_kernel<I8, SG, PK><<<grid, kThreads, smem, st>>>(p);                                      \
   } while (0)
-  if (p.is_int8) { if (single) P4V_LAUNCH(true, true); else P4V_LAUNCH(true, false); }
-  else           { if (single) P4V_LAUNCH(false, true); else P4V_LAUNCH(false, false); }
+#define P4V_LAUNCH2(I8, SG) do { if (packed) P4V_LAUNCH(I8, SG, true); else P4V_LAUNCH(I8, SG, false); } while (0)
+  static const bool packed = [] { const char* e = getenv("P4V_PACKED"); return e ? atoi(e) != 0 : true; }();
+  if (p.is_int8) { if (single) P4V_LAUNCH2(true, true); else P4V_LAUNCH2(true, false); }
+  else           { if (single) P4V_LAUNCH2(false, true); else P4V_LAUNCH2(false, false); }
+#undef P4V_LAUNCH2
 #undef P4V_LAUNCH
   P4V_CUDA_OK(cudaGetLastError());
   return 0;
