@@ -71,6 +71,7 @@ struct SweepParams {
   int is_int8;
   // shared-memory plan, filled by the launcher
   unsigned int stage_r_bytes, stage_c_bytes, n_stages, resident_bytes;
+  long long* trace;         // debug: clock64 timeline of CTA 0 ([3 roles][512 events][4]) or null
 };
 
 static inline __host__ __device__ int p4v_cdiv(int a, int b) { return (a + b - 1) / b; }

@@ -56,7 +56,10 @@ static double sweep_ops(const SweepParams& sp, const P4VJob* host_jobs) {
   const double tiles = (double)sp.P * sp.tiles_m * sp.tiles_n;
   return 2.0 * P4V_TILE * P4V_TILE * tiles * (kf + kc * sp.n_cand);
 }
-int p4v_run_sweep(const SweepParams& sp, const P4VJob* host_jobs, int kernel, cudaStream_t st) {
+static long long* g_trace = nullptr;
+extern "C" __attribute__((visibility("default"))) int p4v_debug_trace(void* dev_ptr) { g_trace = (long long*)dev_ptr; return 0; }
+int p4v_run_sweep(const SweepParams& sp_in, const P4VJob* host_jobs, int kernel, cudaStream_t st) {
+  SweepParams sp = sp_in; sp.trace = g_trace;
   ++g_launches;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (g_prof) { e0 = prof_event(); e1 = prof_event(); cudaEventRecord(e0, st); }

@@ -83,6 +83,13 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// Warp-uniform single-lane election: code guarded by this predicate lets ptxas keep the operands of the
+// async-proxy instructions (UTCHMMA / UTCBAR / UBLKCP) in uniform registers without a per-lane waterfall loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(void* bar) {
@@ -345,88 +352,100 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
   if (warp < 4) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
-    // ======================= TMA producer =======================
-    if (lane == 0) {
+    // ======================= TMA producer (whole warp runs the loop, one elected lane issues) =======================
+    {
       uint32_t stage = 0, phase = 0, rbuf = 0, rphase = 0;
-      auto issue = [&](const P4VJob& j, const Frag& fr, int c) {
-        mbar_wait(&S.empty[stage], phase ^ 1);
-        const uint32_t bytes = (uint32_t)j.kb * P4V_TILE;
-        const size_t rt = (size_t)(fr.p * P.tiles_m + fr.tm), ct = (size_t)(fr.p * P.tiles_n + fr.tn);
-        const uint8_t* cc = ((j.flags & P4V_JOB_CCAND) ? P.C_cand + (size_t)c * P.C_cand_stride + ct * P.C_cand_tile_bytes
-                                                       : P.C_cur + ct * P.C_tile_bytes) + j.c_off;
-        if (j.flags & P4V_JOB_RRES) {
-          mbar_expect_tx(&S.full[stage], bytes);
-        } else {
-          const uint8_t* r = ((j.flags & P4V_JOB_RCAND) ? P.R_cand + (size_t)c * P.R_cand_stride + rt * P.R_cand_tile_bytes
-                                                        : P.R_cur + rt * P.R_tile_bytes) + j.r_off;
-          mbar_expect_tx(&S.full[stage], 2 * bytes);
-          bulk_g2s(ringR + stage * sR, r, bytes, &S.full[stage]);
-        }
-        bulk_g2s(ringC + stage * sC, cc, bytes, &S.full[stage]);
-        if (++stage == nst) { stage = 0; phase ^= 1; }
-      };
       while (next_frag(P, sched, f)) {
+        const size_t rt = (size_t)(f.p * P.tiles_m + f.tm), ct = (size_t)(f.p * P.tiles_n + f.tn);
+        const uint8_t* r_cur = P.R_cur + rt * P.R_tile_bytes;
+        const uint8_t* c_cur = P.C_cur + ct * P.C_tile_bytes;
+        const uint8_t* r_cand = P.R_cand + rt * P.R_cand_tile_bytes;
+        const uint8_t* c_cand = P.C_cand + ct * P.C_cand_tile_bytes;
         if (resB) {      // row operand of the candidate jobs: once per fragment, reused by every candidate
           mbar_wait(&S.res_empty[rbuf], rphase ^ 1);
           uint32_t total = 0;
           for (int j = 0; j < P.n_cand_jobs; ++j) total += (uint32_t)S.jobs[P.n_fixed_jobs + j].kb * P4V_TILE;
-          mbar_expect_tx(&S.res_full[rbuf], total);
-          const uint8_t* rbase = P.R_cur + (size_t)(f.p * P.tiles_m + f.tm) * P.R_tile_bytes;
-          for (int j = 0; j < P.n_cand_jobs; ++j) {
-            const P4VJob& jb = S.jobs[P.n_fixed_jobs + j];
-            bulk_g2s(resR + rbuf * resB + jb.res_off, rbase + jb.r_off, (uint32_t)jb.kb * P4V_TILE, &S.res_full[rbuf]);
+          if (elect_one()) {
+            mbar_expect_tx(&S.res_full[rbuf], total);
+            for (int j = 0; j < P.n_cand_jobs; ++j) {
+              const P4VJob jb = S.jobs[P.n_fixed_jobs + j];
+              bulk_g2s(resR + rbuf * resB + jb.res_off, r_cur + jb.r_off, (uint32_t)jb.kb * P4V_TILE, &S.res_full[rbuf]);
+            }
           }
+          __syncwarp();
           if (++rbuf == 2) { rbuf = 0; rphase ^= 1; }
         }
-        for (int j = 0; j < P.n_fixed_jobs; ++j) issue(S.jobs[j], f, 0);
-        for (int c = f.c0; c < f.c1; ++c)
-          for (int j = 0; j < P.n_cand_jobs; ++j) issue(S.jobs[P.n_fixed_jobs + j], f, c);
+        const int n_issue = P.n_fixed_jobs + (f.c1 - f.c0) * P.n_cand_jobs;
+        int jidx = 0, c = f.c0;
+        for (int it = 0; it < n_issue; ++it) {
+          const bool is_fixed = it < P.n_fixed_jobs;
+          const P4VJob j = S.jobs[is_fixed ? it : P.n_fixed_jobs + jidx];
+          mbar_wait(&S.empty[stage], phase ^ 1);
+          const uint32_t bytes = (uint32_t)j.kb * P4V_TILE;
+          const uint8_t* cc = ((j.flags & P4V_JOB_CCAND) ? c_cand + (size_t)c * P.C_cand_stride : c_cur) + j.c_off;
+          const uint8_t* rr = ((j.flags & P4V_JOB_RCAND) ? r_cand + (size_t)c * P.R_cand_stride : r_cur) + j.r_off;
+          if (elect_one()) {
+            if (j.flags & P4V_JOB_RRES) {
+              mbar_expect_tx(&S.full[stage], bytes);
+            } else {
+              mbar_expect_tx(&S.full[stage], 2 * bytes);
+              bulk_g2s(ringR + stage * sR, rr, bytes, &S.full[stage]);
+            }
+            bulk_g2s(ringC + stage * sC, cc, bytes, &S.full[stage]);
+          }
+          __syncwarp();
+          if (++stage == nst) { stage = 0; phase ^= 1; }
+          if (!is_fixed && ++jidx == P.n_cand_jobs) { jidx = 0; ++c; }
+        }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    // ======================= MMA issuer =======================
-    if (lane == 0) {
+    // ======================= MMA issuer (whole warp runs the loop, one elected lane issues) =======================
+    {
       uint32_t stage = 0, phase = 0, slot = 0, slot_phase = 0, rbuf = 0, rphase = 0;
-      auto run = [&](const P4VJob& j, uint32_t res_base) {
-        if (j.flags & P4V_JOB_FIRST) {
-          mbar_wait(&S.acc_empty[slot], slot_phase ^ 1);
-          tc_fence_after();
-        }
-        mbar_wait(&S.full[stage], phase);
-        tc_fence_after();
-        const uint32_t ra = (j.flags & P4V_JOB_RRES) ? res_base + j.res_off : ringR + stage * sR;
-        const uint32_t ca = ringC + stage * sC;
-        const uint32_t d = tmem + kAccBase + slot * kAccCols;
-        const int ksteps = j.kb >> 5;
-        for (int k = 0; k < ksteps; ++k) {
-          uint32_t acc = ((j.flags & P4V_JOB_FIRST) && k == 0) ? 0u : 1u;
-          umma<kInt8>(d, make_desc(ra + k * 2 * P4V_TILE * 16), make_desc(ca + k * 2 * P4V_TILE * 16), acc);
-        }
-        tc_commit(&S.empty[stage]);
-        if (j.flags & P4V_JOB_LAST) {
-          tc_commit(&S.acc_full[slot]);
-          if (++slot == kSlots) { slot = 0; slot_phase ^= 1; }
-        }
-        if (++stage == nst) { stage = 0; phase ^= 1; }
-      };
+      int tr_n = 0;
       while (next_frag(P, sched, f)) {
-        for (int j = 0; j < P.n_fixed_jobs; ++j) run(S.jobs[j], 0);
         uint32_t res_base = 0;
-        if (resB) {
-          mbar_wait(&S.res_full[rbuf], rphase);
+        const int n_issue = P.n_fixed_jobs + (f.c1 - f.c0) * P.n_cand_jobs;
+        int jidx = 0;
+        for (int it = 0; it < n_issue; ++it) {
+          const bool is_fixed = it < P.n_fixed_jobs;
+          if (resB && it == P.n_fixed_jobs) {       // first candidate job of the fragment: resident row operand landed?
+            mbar_wait(&S.res_full[rbuf], rphase);
+            res_base = resR + rbuf * resB;
+          }
+          const P4VJob j = S.jobs[is_fixed ? it : P.n_fixed_jobs + jidx];
+          const long long tr0 = P.trace ? clock64() : 0;
+          if (j.flags & P4V_JOB_FIRST) mbar_wait(&S.acc_empty[slot], slot_phase ^ 1);
+          mbar_wait(&S.full[stage], phase);
           tc_fence_after();
-          res_base = resR + rbuf * resB;
+          const long long tr1 = P.trace ? clock64() : 0;
+          const uint32_t ra = (j.flags & P4V_JOB_RRES) ? res_base + j.res_off : ringR + stage * sR;
+          const uint32_t ca = ringC + stage * sC;
+          const uint32_t d = tmem + kAccBase + slot * kAccCols;
+          const int ksteps = j.kb >> 5;
+          if (elect_one()) {
+            for (int k = 0; k < ksteps; ++k)
+              umma<kInt8>(d, make_desc(ra + k * 2 * P4V_TILE * 16), make_desc(ca + k * 2 * P4V_TILE * 16),
+                          ((j.flags & P4V_JOB_FIRST) && k == 0) ? 0u : 1u);
+            tc_commit(&S.empty[stage]);
+            if (j.flags & P4V_JOB_LAST) tc_commit(&S.acc_full[slot]);
+          }
+          __syncwarp();
+          if (P.trace && blockIdx.x == 0 && lane == 0 && tr_n < 512) {
+            long long* e = P.trace + (1 * 512 + tr_n) * 4; e[0] = tr0; e[1] = tr1; e[2] = clock64(); e[3] = it; ++tr_n;
+          }
+          if (j.flags & P4V_JOB_LAST) { if (++slot == kSlots) { slot = 0; slot_phase ^= 1; } }
+          if (++stage == nst) { stage = 0; phase ^= 1; }
+          if (!is_fixed && ++jidx == P.n_cand_jobs) jidx = 0;
         }
-        for (int c = f.c0; c < f.c1; ++c)
-          for (int j = 0; j < P.n_cand_jobs; ++j) run(S.jobs[P.n_fixed_jobs + j], res_base);
         if (resB) {
-          tc_commit(&S.res_empty[rbuf]);           // resident buffer free once every MMA reading it has retired
+          if (elect_one()) tc_commit(&S.res_empty[rbuf]);   // resident buffer free once every MMA reading it has retired
+          __syncwarp();
           if (++rbuf == 2) { rbuf = 0; rphase ^= 1; }
         }
       }
     }
-    __syncwarp();
   }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
