@@ -18,7 +18,7 @@
 
 #define P4V_TILE 128           // rows per operand tile == UMMA M == UMMA N
 #define P4V_JOB_KB 128         // max bytes of K per row and job
-#define P4V_MAX_JOBS 192
+#define P4V_MAX_JOBS 320
 #define P4V_MAX_GROUPS 96
 #define P4V_MAX_CAND 128
 #define P4V_CG 16              // columns per scale / score group
@@ -66,7 +66,8 @@ struct SweepParams {
   unsigned long long cand_noA_mask;   // bit g set: candidate group g ignores candA (scale = candB only)
   int n_cand;
   float* partial;           // [tiles_total][n_cand][4][8]
-  float* out;               // if non-null: write bias + sum(scale*acc) of the fixed groups (quant_forward), no candidates
+  float* out;               // if non-null: no candidates; write bias + sum(scale*acc) of the fixed groups (quant_forward)
+  int out_residual;         // with out: write y - bias - sum(scale*acc) instead (the current residual e)
   int order;                // 0: tile_m fastest, 1: tile_n fastest
   int is_int8;
   // shared-memory plan, filled by the launcher

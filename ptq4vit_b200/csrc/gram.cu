@@ -1,0 +1,311 @@
+// Normal-equation ("Gram") form of the weight-step search for narrow column blocks.
+//
+// For column block h, row block v and candidate c the reference evaluates
+//     score_c[v] = - sum_{m, o in v} ( g[m,o] * ( y[m,o] - yhat_c[m,o] ) )^2          (linear.py:417-423, :466-488)
+// and yhat_c differs from the current quantised output only through the ks = K/n_H weights of block h:
+//     y - yhat_c = e - xhat_h * (w_c - w_cur)^T ,   e = y - yhat_cur ,  xhat_h = fake-quantised x[:, block h].
+// Expanding the square per output channel o with d = w_c[o,:] - w_cur[o,:] (ks numbers):
+//     sum_m (g e)^2  -  2 d . U[o]  +  d^T H[o] d ,   U[o] = sum_m g^2 e xhat ,  H[o] = sum_m g^2 xhat xhat^T .
+// All three terms are of the size of the quantisation error (no cancellation; fp32 reproduces the reference's
+// score tables to 2e-7, see tests).  H is a contraction over the TOKENS, so it runs as one tensor-core GEMM
+// (g^2)^T[O x M] . Z[M x ks(ks+1)/2] per step -- the candidates never touch TMEM or HBM again: evaluating all
+// eq_n candidates costs eq_n * O * ks^2/2 FMAs.  This removes the TMEM->register read of one 128x128 accumulator
+// per candidate and tile (64 B/clk/SM, the limit of the direct sweep).
+#include "gram.cuh"
+
+void p4v_count_launch();
+
+namespace {
+
+__device__ __forceinline__ float fq_dev(float w, float delta, float lo, float hi) {
+  return fminf(fmaxf(rintf(__fdiv_rn(w, delta)), lo), hi) * delta;
+}
+
+// x [M][K] fp32 -> XqT [K][Mp] int8 (quantised with the current activation step sizes)
+__global__ void xq_transpose_kernel(const float* __restrict__ x, int M, int K, int Mp, const float* __restrict__ dX,
+                                    int crb_acts, float qlo, float qhi, int8_t* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int m0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int m = m0 + i, k = k0 + threadIdx.x;
+    tile[i][threadIdx.x] = (m < M && k < K) ? x[(size_t)m * K + k] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int k = k0 + i, m = m0 + threadIdx.x;
+    if (k < K && m < Mp) {
+      float q = 0.f;
+      if (m < M) {
+        q = fminf(fmaxf(rintf(__fdiv_rn(tile[threadIdx.x][i], dX[k / crb_acts])), qlo), qhi);
+        if (!(q == q)) q = 0.f;
+      }
+      out[(size_t)k * Mp + m] = (int8_t)(int)q;
+    }
+  }
+}
+
+// Z image: rows = pairs (k <= k') of the slab, K = tokens; value = Xq[m,k] * Xq[m,k'] split exactly into two bf16 terms.
+// image layout [tile][chunk][128][16 B] ; hi term at byte offset 0 of the padded row, lo term at term_bytes.
+__global__ void pair_image_kernel(const int8_t* __restrict__ XqT, int Mp, int M, int k_first, int ks, int npairs,
+                                  int tiles_p, unsigned long long tile_bytes, unsigned int term_bytes, uint8_t* __restrict__ dst) {
+  const int rows_pad = tiles_p * P4V_TILE;
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;        // pair index (padded)
+  const int chunk = blockIdx.y;                                  // 8 tokens
+  if (row >= rows_pad) return;
+  uint32_t hi[4] = {0, 0, 0, 0}, lo[4] = {0, 0, 0, 0};
+  if (row < npairs) {
+    // invert p = k*ks - k(k-1)/2 + (k' - k)
+    int k = 0, base = 0;
+    while (base + (ks - k) <= row) { base += ks - k; ++k; }
+    const int k2 = k + (row - base);
+    const int8_t* a = XqT + (size_t)(k_first + k) * Mp + chunk * 8;
+    const int8_t* b = XqT + (size_t)(k_first + k2) * Mp + chunk * 8;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int m = chunk * 8 + e;
+      const float z = m < M ? (float)((int)a[e] * (int)b[e]) : 0.f;
+      const __nv_bfloat16 h = __float2bfloat16_rn(z);
+      const __nv_bfloat16 l = __float2bfloat16_rn(z - __bfloat162float(h));     // |z| < 2^15: two terms are exact
+      hi[e >> 1] |= (uint32_t)__bfloat16_as_ushort(h) << ((e & 1) * 16);
+      lo[e >> 1] |= (uint32_t)__bfloat16_as_ushort(l) << ((e & 1) * 16);
+    }
+  }
+  const int tile = row / P4V_TILE, r = row % P4V_TILE;
+  uint8_t* base_p = dst + (size_t)tile * tile_bytes + ((size_t)chunk * P4V_TILE + r) * 16;
+  *reinterpret_cast<uint4*>(base_p) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(base_p + (size_t)term_bytes * P4V_TILE) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+// One pass over e and g: apply the rank-ks update of the previous step, accumulate U and sum (g e)^2 for the next slab.
+// block = 128 output channels x GRAM_BM tokens; thread = one output channel.
+template <int KS>
+__global__ void __launch_bounds__(128) gram_update_kernel(const GramUpdateArgs a) {
+  extern __shared__ float sm[];
+  float* xp = sm;                       // [BM][KS] previous slab (xhat), only if a.h_prev >= 0
+  float* xn = sm + GRAM_BM * KS;        // [BM][KS] next slab
+  const int o = blockIdx.x * 128 + threadIdx.x;
+  const int m0 = blockIdx.y * GRAM_BM;
+  const int rows = min(GRAM_BM, a.M - m0);
+  const float gs = a.gscale[0];
+  const bool has_prev = a.h_prev >= 0;
+  // slab tiles of the token-major int8 activations -> fp32 xhat in shared memory ([token][k], k contiguous).
+  // thread = (k, 16-token chunk): one 16-byte load per slab row segment, conflict-free stores (lanes = consecutive k).
+  for (int it = threadIdx.x; it < KS * (GRAM_BM / 16); it += 128) {
+    const int k = it % KS, ch = it / KS;
+    const int mm0 = ch * 16;
+    float vn[16], vp[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) { vn[e] = 0.f; vp[e] = 0.f; }
+    if (k < a.ks && mm0 < rows) {
+      const float dn = a.dX[(a.k_next + k) / a.crb_acts];
+      const int4 qn = *reinterpret_cast<const int4*>(a.XqT + (size_t)(a.k_next + k) * a.Mp + m0 + mm0);
+      const int8_t* bn = reinterpret_cast<const int8_t*>(&qn);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) vn[e] = (mm0 + e < rows) ? dn * (float)bn[e] : 0.f;
+      if (has_prev) {
+        const float dp = a.dX[(a.k_prev + k) / a.crb_acts];
+        const int4 qp = *reinterpret_cast<const int4*>(a.XqT + (size_t)(a.k_prev + k) * a.Mp + m0 + mm0);
+        const int8_t* bp = reinterpret_cast<const int8_t*>(&qp);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) vp[e] = (mm0 + e < rows) ? dp * (float)bp[e] : 0.f;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 16; ++e) { xn[(mm0 + e) * KS + k] = vn[e]; xp[(mm0 + e) * KS + k] = vp[e]; }
+  }
+  float delta[KS], acc[KS];
+#pragma unroll
+  for (int k = 0; k < KS; ++k) { delta[k] = 0.f; acc[k] = 0.f; }
+  if (has_prev && o < a.O) {
+    const int v = min(o / a.crb_rows, a.n_V - 1);
+    const float d_new = a.dW[v * a.n_H + a.h_prev], d_old = a.dW_prev[v];
+    const float* wrow = a.W + (size_t)o * a.K + a.k_prev;
+#pragma unroll
+    for (int k = 0; k < KS; ++k)
+      if (k < a.ks) delta[k] = fq_dev(wrow[k], d_new, a.w_lo, a.w_hi) - fq_dev(wrow[k], d_old, a.w_lo, a.w_hi);
+  }
+  __syncthreads();
+  float e2 = 0.f;
+  if (o < a.O) {
+    constexpr int UN = 16;                                  // tokens in flight per thread (hides the HBM latency)
+    for (int mm0 = 0; mm0 < rows; mm0 += UN) {
+      float ev[UN], gv[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const bool ok = mm0 + u < rows;
+        const size_t off = (size_t)(m0 + mm0 + u) * a.O + o;
+        ev[u] = ok ? a.E[off] : 0.f;
+        gv[u] = ok ? a.G[off] * gs : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int mm = mm0 + u;
+        if (mm < rows) {
+          float e = ev[u];
+          if (has_prev) {
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;      // four independent chains
+#pragma unroll
+            for (int k = 0; k < KS; k += 4) {
+              const float4 xv = *reinterpret_cast<const float4*>(&xp[mm * KS + k]);
+              s0 = fmaf(xv.x, delta[k], s0); s1 = fmaf(xv.y, delta[k + 1], s1);
+              s2 = fmaf(xv.z, delta[k + 2], s2); s3 = fmaf(xv.w, delta[k + 3], s3);
+            }
+            e -= (s0 + s1) + (s2 + s3);
+            a.E[(size_t)(m0 + mm) * a.O + o] = e;
+          }
+          const float ge = gv[u] * e;
+          e2 = fmaf(ge, ge, e2);
+          const float w = gv[u] * ge;
+#pragma unroll
+          for (int k = 0; k < KS; k += 4) {
+            const float4 xv = *reinterpret_cast<const float4*>(&xn[mm * KS + k]);
+            acc[k] = fmaf(w, xv.x, acc[k]); acc[k + 1] = fmaf(w, xv.y, acc[k + 1]);
+            acc[k + 2] = fmaf(w, xv.z, acc[k + 2]); acc[k + 3] = fmaf(w, xv.w, acc[k + 3]);
+          }
+        }
+      }
+    }
+    float* up = a.Upart + ((size_t)blockIdx.y * a.O + o) * a.ks;
+#pragma unroll
+    for (int k = 0; k < KS; ++k) if (k < a.ks) up[k] = acc[k];
+    a.E2part[(size_t)blockIdx.y * a.O + o] = e2;
+  }
+}
+
+// U[o][k] = sum over token blocks (fixed order), E2[o] likewise.  thread = (o, k) ; k == ks handles E2.
+__global__ void gram_reduce_kernel(const float* __restrict__ Upart, const float* __restrict__ E2part, int n_mblk, int O, int ks,
+                                   float* __restrict__ U, float* __restrict__ E2) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nU = (long long)O * ks;
+  if (i < nU) {
+    float s = 0.f;
+    for (int b = 0; b < n_mblk; ++b) s += Upart[(size_t)b * nU + i];
+    U[i] = s;
+  } else if (i < nU + O) {
+    const int o = (int)(i - nU);
+    float s = 0.f;
+    for (int b = 0; b < n_mblk; ++b) s += E2part[(size_t)b * O + o];
+    E2[o] = s;
+  }
+}
+
+// sums2[c][v] = sum over the osplit thread-block partials of row block v (fixed order).
+__global__ void gram_keysum_kernel(const double* __restrict__ sums, int n_cand, int n_groups, int osplit, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_cand * n_groups) return;
+  const int c = i / n_groups, v = i % n_groups;
+  const double* p = sums + ((size_t)c * n_groups + v) * osplit;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int k = 0;
+  for (; k + 4 <= osplit; k += 4) { s0 += p[k]; s1 += p[k + 1]; s2 += p[k + 2]; s3 += p[k + 3]; }
+  for (; k < osplit; ++k) s0 += p[k];
+  out[i] = (s0 + s1) + (s2 + s3);
+}
+
+// block = a slice of one row block v (a.rows_per_block channels), thread = candidate.
+// sums[c][block] = sum_o ( E2 - 2 d.U + d^T H d ).
+template <int KS>
+__global__ void __launch_bounds__(128) gram_eval_kernel(const GramEvalArgs a) {
+  extern __shared__ float sm[];
+  float* Hs = sm;                        // [npairs]
+  float* Us = Hs + a.npairs;             // [KS]
+  float* Ws = Us + KS;                   // [KS] fp32 weights of this channel
+  float* Wc = Ws + KS;                   // [KS] currently quantised weights
+  __shared__ float e2s;
+  const int v = blockIdx.x / a.osplit, part = blockIdx.x % a.osplit;
+  const int c = threadIdx.x;
+  const int o_begin = v * a.rows_per_group + part * a.rows_per_block;
+  const int o_end = min(min(a.O, (v + 1) * a.rows_per_group), o_begin + a.rows_per_block);
+  const float d_cur = a.dW[v * a.n_H + a.h];
+  const float d_c = c < a.n_cand ? a.factors[c] * a.dW0[v * a.n_H + a.h] : 1.f;
+  const float dx = a.dX[a.k_first / a.crb_acts];
+  const float dx2 = dx * dx;
+  double total = 0.0;
+  for (int o = o_begin; o < o_end; ++o) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < a.npairs; i += blockDim.x) Hs[i] = a.H[(size_t)o * a.ldH + i] * dx2;
+    for (int k = threadIdx.x; k < a.ks; k += blockDim.x) {
+      Us[k] = a.U[(size_t)o * a.ks + k];
+      const float w = a.W[(size_t)o * a.K + a.k_first + k];
+      Ws[k] = w; Wc[k] = fq_dev(w, d_cur, a.w_lo, a.w_hi);
+    }
+    if (threadIdx.x == 0) e2s = a.E2[o];
+    __syncthreads();
+    if (c < a.n_cand) {
+      float d[KS];
+#pragma unroll
+      for (int k = 0; k < KS; ++k) d[k] = k < a.ks ? fq_dev(Ws[k], d_c, a.w_lo, a.w_hi) - Wc[k] : 0.f;
+      float lin = 0.f, quad = 0.f;
+      int p = 0;
+#pragma unroll
+      for (int k = 0; k < KS; ++k) {
+        if (k < a.ks) {
+          lin = fmaf(d[k], Us[k], lin);
+          float row = 0.5f * d[k] * Hs[p];                       // diagonal counted once
+#pragma unroll
+          for (int k2 = k + 1; k2 < KS; ++k2)
+            if (k2 < a.ks) row = fmaf(d[k2], Hs[p + (k2 - k)], row);
+          quad = fmaf(2.f * d[k], row, quad);
+          p += a.ks - k;
+        }
+      }
+      total += (double)(e2s - 2.f * lin + quad);
+    }
+  }
+  if (c < a.n_cand) a.sums[(size_t)c * a.n_keys + blockIdx.x] = total;
+}
+
+}  // namespace
+
+int p4v_xq_transpose(const float* x, int M, int K, int Mp, const float* dX, int crb_acts, float qlo, float qhi, int8_t* out,
+                     cudaStream_t st) {
+  dim3 grid(p4v_cdiv(Mp, 32), p4v_cdiv(K, 32)), block(32, 8);
+  xq_transpose_kernel<<<grid, block, 0, st>>>(x, M, K, Mp, dX, crb_acts, qlo, qhi, out); p4v_count_launch();
+  P4V_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int p4v_pair_image(const int8_t* XqT, int Mp, int M, int k_first, int ks, int npairs, int tiles_p, unsigned long long tile_bytes,
+                   unsigned int term_bytes, uint8_t* dst, cudaStream_t st) {
+  dim3 grid(tiles_p, term_bytes / 16);
+  pair_image_kernel<<<grid, 128, 0, st>>>(XqT, Mp, M, k_first, ks, npairs, tiles_p, tile_bytes, term_bytes, dst); p4v_count_launch();
+  P4V_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+template <int KS> static int launch_update(const GramUpdateArgs& a, cudaStream_t st) {
+  dim3 grid(p4v_cdiv(a.O, 128), p4v_cdiv(a.M, GRAM_BM));
+  const size_t smem = (size_t)2 * GRAM_BM * KS * sizeof(float);
+  P4V_CUDA_OK(cudaFuncSetAttribute(gram_update_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  gram_update_kernel<KS><<<grid, 128, smem, st>>>(a); p4v_count_launch();
+  P4V_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int p4v_gram_update(const GramUpdateArgs& a, cudaStream_t st) {
+  P4V_REQUIRE(a.ks <= 64 && a.ks % 4 == 0, "gram: column block must be a multiple of 4 and <= 64 (got %d)", a.ks);
+  if (a.ks <= 32) return launch_update<32>(a, st);
+  return launch_update<64>(a, st);
+}
+
+int p4v_gram_reduce(const float* Upart, const float* E2part, int n_mblk, int O, int ks, float* U, float* E2, cudaStream_t st) {
+  const long long n = (long long)O * ks + O;
+  gram_reduce_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Upart, E2part, n_mblk, O, ks, U, E2); p4v_count_launch();
+  P4V_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+template <int KS> static int launch_eval(const GramEvalArgs& a, cudaStream_t st) {
+  const size_t smem = ((size_t)a.npairs + 3 * KS) * sizeof(float);
+  P4V_CUDA_OK(cudaFuncSetAttribute(gram_eval_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  gram_eval_kernel<KS><<<a.n_groups * a.osplit, 128, smem, st>>>(a); p4v_count_launch();
+  P4V_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int p4v_gram_eval(const GramEvalArgs& a, cudaStream_t st) {
+  P4V_REQUIRE(a.n_cand <= 128, "gram: at most 128 candidates");
+  int rc = a.ks <= 32 ? launch_eval<32>(a, st) : launch_eval<64>(a, st);
+  if (rc) return rc;
+  gram_keysum_kernel<<<p4v_cdiv(a.n_cand * a.n_groups, 256), 256, 0, st>>>(a.sums, a.n_cand, a.n_groups, a.osplit, a.sums2); p4v_count_launch();
+  P4V_CUDA_OK(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,38 @@
+// Normal-equation form of the weight-step search (see gram.cu).
+#pragma once
+#include "common.cuh"
+
+#define GRAM_BM 128      // tokens per block of the update pass
+
+struct GramUpdateArgs {
+  float* E; const float* G; const float* gscale;      // [M][O] residual (in/out), gradient, power-of-two scale
+  const float* W; int M, O, K;
+  const int8_t* XqT; int Mp;                           // [K][Mp] quantised activations, token-major
+  const float* dX; int crb_acts;
+  const float* dW; const float* dW_prev;               // current table [n_V][n_H]; step sizes of block h_prev before its search [n_V]
+  int n_V, n_H, crb_rows;
+  int h_prev, k_prev, k_next, ks;                      // h_prev < 0: no update, only accumulate
+  float w_lo, w_hi;
+  float* Upart; float* E2part;                         // [n_mblk][O][ks], [n_mblk][O]
+};
+int p4v_gram_update(const GramUpdateArgs& a, cudaStream_t st);
+
+struct GramEvalArgs {
+  const float* H; int ldH; int npairs;                 // [O][ldH] Gram of the integer activations (upper triangle, row-major pairs)
+  const float* U; const float* E2;                     // [O][ks], [O] (reduced over the token blocks)
+  const float* W; int O, K, k_first, ks;
+  const float* dW; const float* dW0; int n_H, h;
+  const float* dX; int crb_acts;
+  const float* factors; int n_cand;
+  int n_groups, rows_per_group;                        // row blocks v
+  int osplit, rows_per_block;                          // each row block is evaluated by osplit thread blocks of rows_per_block channels
+  float w_lo, w_hi;
+  double* sums; int n_keys;                            // [n_cand][n_keys = n_groups*osplit]: positive error sums per thread block
+  double* sums2;                                       // [n_cand][n_groups]: the same summed per row block
+};
+int p4v_gram_eval(const GramEvalArgs& a, cudaStream_t st);
+int p4v_gram_reduce(const float* Upart, const float* E2part, int n_mblk, int O, int ks, float* U, float* E2, cudaStream_t st);
+
+int p4v_xq_transpose(const float* x, int M, int K, int Mp, const float* dX, int crb_acts, float qlo, float qhi, int8_t* out, cudaStream_t st);
+int p4v_pair_image(const int8_t* XqT, int Mp, int M, int k_first, int ks, int npairs, int tiles_p, unsigned long long tile_bytes,
+                   unsigned int term_bytes, uint8_t* dst, cudaStream_t st);

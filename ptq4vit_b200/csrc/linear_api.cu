@@ -4,10 +4,12 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <vector>
 
 #include "../../include/ptq4vit_b200.h"
 #include "prep.cuh"
+#include "gram.cuh"
 
 int p4v_num_sms();
 
@@ -97,6 +99,11 @@ struct LinPlan {
   std::vector<P4VSeg> segsW, segsX, segsXc;
   std::vector<Step> wsteps, xsteps;
   Step fwd;   // quant_forward: every segment is a fixed group
+  // normal-equation W search (gram.cu)
+  bool gram; int g_ks, g_Mp, g_npairs, g_tiles_p, g_ldH, g_nmblk, g_njobs; unsigned g_term_bytes;
+  std::vector<P4VJob> gjobs;
+  size_t o_E, o_XqT, o_G2T, o_Z, o_H, o_Upart, o_E2part, o_U, o_E2, o_dprev, o_ones, o_gjobs, o_segsG;
+  int g_osplit, g_opb;
   std::vector<float> factors;
   int max_groups;
   // workspace offsets
@@ -181,16 +188,16 @@ int build_plan(const p4v_linear_desc* d, LinPlan& p, bool with_search) {
   // quantisation segment tables
   p.segsW.clear(); p.segsX.clear(); p.segsXc.clear();
   for (auto& s : p.segs) {
-    P4VSeg w{s.k0, s.klen, s.woff * P4V_TILE, s.h, 0.f, (float)-p.w_qmax, (float)(p.w_qmax - 1), 0, 0.f, 0};
+    P4VSeg w{s.k0, s.klen, s.woff * P4V_TILE, s.h, 0.f, (float)-p.w_qmax, (float)(p.w_qmax - 1), 0, 0.f, 0, 0};
     p.segsW.push_back(w);
-    P4VSeg x{s.k0, s.klen, s.xoff_p * P4V_TILE, s.a, 0.f, p.twin ? 0.f : (float)-p.a_qmax, (float)(p.a_qmax - 1), 0, 0.f, 0};
+    P4VSeg x{s.k0, s.klen, s.xoff_p * P4V_TILE, s.a, 0.f, p.twin ? 0.f : (float)-p.a_qmax, (float)(p.a_qmax - 1), 0, 0.f, 0, 0};
     p.segsX.push_back(x);
     P4VSeg xc = x; xc.dst_off = s.xcoff * P4V_TILE;
     p.segsXc.push_back(xc);
   }
   if (p.twin)
     for (auto& s : p.segs) {
-      P4VSeg n{s.k0, s.klen, s.xoff_n * P4V_TILE, s.a, p.d_neg, (float)-p.a_qmax, 0.f, 0, 0.f, 0};
+      P4VSeg n{s.k0, s.klen, s.xoff_n * P4V_TILE, s.a, p.d_neg, (float)-p.a_qmax, 0.f, 0, 0.f, 0, 0};
       p.segsX.push_back(n);
     }
 
@@ -264,7 +271,7 @@ int build_plan(const p4v_linear_desc* d, LinPlan& p, bool with_search) {
   p.o_dW0 = take(d->n_V * d->n_H * 4); p.o_dW = take(d->n_V * d->n_H * 4);
   p.o_dX0 = take(d->n_a * 4); p.o_dX = take(d->n_a * 4);
   p.o_gscale = take(4);
-  p.o_scores = take((size_t)n_c * p.nsg * 8);
+  p.o_scores = take((size_t)n_c * (p.nsg + d->n_V * (size_t)(1 + p4v_cdiv(p.crb_rows, 2))) * 8);
   p.o_best = take(std::max(d->n_V, 1) * 4);
   p.o_fix = take((size_t)p.max_groups * p.nsg * 4);
   p.o_candA = take((size_t)n_c * p.nsg * 4);
@@ -280,6 +287,48 @@ int build_plan(const p4v_linear_desc* d, LinPlan& p, bool with_search) {
   p.o_Xcur = take((size_t)p.tiles_m * P4V_TILE * p.KB_X);
   p.o_Wcand = take(with_search ? (size_t)n_c * p.tiles_o * P4V_TILE * p.KB_W : 4);
   p.o_Xcand = take(with_search ? (size_t)n_c * p.tiles_m * P4V_TILE * p.KB_Xc : 4);
+  // normal-equation W search: narrow column blocks inside one activation chunk, plain (non twin) activations
+  p.gram = false;
+  {
+    const char* env = getenv("P4V_GRAM");
+    const bool want = with_search && (env ? atoi(env) != 0 : true) && d->kernel == P4V_KERNEL_TCGEN05;
+    const unsigned term = (unsigned)align_up((size_t)p.M * 2, 32);
+    const int nj = (int)((term + P4V_JOB_KB - 1) / P4V_JOB_KB);
+    if (want && !p.twin && p.crb_cols <= 64 && p.crb_cols % 4 == 0 && p.crb_acts % p.crb_cols == 0 && 3 * nj <= P4V_MAX_JOBS) {
+      p.gram = true;
+      p.g_ks = p.crb_cols; p.g_term_bytes = term; p.g_njobs = nj;
+      p.g_Mp = (int)align_up((size_t)p.M, 16) + 16;
+      p.g_npairs = p.g_ks * (p.g_ks + 1) / 2;
+      p.g_tiles_p = p4v_cdiv(p.g_npairs, P4V_TILE); p.g_ldH = p.g_tiles_p * P4V_TILE;
+      p.g_nmblk = p4v_cdiv(p.M, GRAM_BM);
+      p.gjobs.clear();
+      const int combos[3][2] = {{0, 0}, {0, 1}, {1, 0}};          // (g^2 term, Z term): hi*hi + hi*lo + lo*hi
+      for (int gi = 0; gi < 3; ++gi)
+        for (int j = 0; j < nj; ++j) {
+          P4VJob jb{};
+          const unsigned b = (unsigned)j * P4V_JOB_KB;
+          jb.r_off = (combos[gi][0] * term + b) * P4V_TILE; jb.c_off = (combos[gi][1] * term + b) * P4V_TILE;
+          jb.kb = (uint16_t)std::min<unsigned>(P4V_JOB_KB, term - b);
+          jb.flags = (j == 0 ? P4V_JOB_FIRST : 0) | (j == nj - 1 ? P4V_JOB_LAST : 0);
+          jb.group = (uint8_t)gi;
+          p.gjobs.push_back(jb);
+        }
+      const size_t KBg = 2 * (size_t)term;
+      p.o_E = take((size_t)p.M * p.O * 4);
+      p.o_XqT = take((size_t)p.K * p.g_Mp);
+      p.o_G2T = take((size_t)p.tiles_o * P4V_TILE * KBg);
+      p.o_Z = take((size_t)p.g_tiles_p * P4V_TILE * KBg);
+      p.o_H = take((size_t)p.O * p.g_ldH * 4);
+      p.o_Upart = take((size_t)p.g_nmblk * p.O * p.g_ks * 4);
+      p.o_E2part = take((size_t)p.g_nmblk * p.O * 4);
+      p.o_U = take((size_t)p.O * p.g_ks * 4); p.o_E2 = take((size_t)p.O * 4);
+      p.g_osplit = std::max(1, p4v_cdiv(p.crb_rows, 2)); p.g_opb = p4v_cdiv(p.crb_rows, p.g_osplit);
+      p.o_dprev = take((size_t)d->n_V * 4);
+      p.o_ones = take((size_t)3 * p.g_tiles_p * P4V_TILE_CG * 4);
+      p.o_gjobs = take(p.gjobs.size() * sizeof(P4VJob));
+      p.o_segsG = take(2 * sizeof(P4VSeg));
+    }
+  }
   p.total = o;
   return 0;
 }
@@ -295,6 +344,13 @@ int upload_tables(const LinPlan& p, void* ws, cudaStream_t st) {
   P4V_CUDA_OK(cudaMemcpyAsync(at<void>(ws, p.o_segsXc), p.segsXc.data(), p.segsXc.size() * sizeof(P4VSeg), cudaMemcpyHostToDevice, st));
   if (!p.commits.empty())
     P4V_CUDA_OK(cudaMemcpyAsync(at<void>(ws, p.o_commits), p.commits.data(), p.commits.size() * sizeof(CommitSeg), cudaMemcpyHostToDevice, st));
+  if (p.gram) {
+    P4V_CUDA_OK(cudaMemcpyAsync(at<void>(ws, p.o_gjobs), p.gjobs.data(), p.gjobs.size() * sizeof(P4VJob), cudaMemcpyHostToDevice, st));
+    std::vector<float> ones((size_t)3 * p.g_tiles_p * P4V_TILE_CG, 1.f);
+    P4V_CUDA_OK(cudaMemcpyAsync(at<void>(ws, p.o_ones), ones.data(), ones.size() * 4, cudaMemcpyHostToDevice, st));
+    P4VSeg sg[2] = {{0, p.M, 0, 0, 0.f, 0.f, 0.f, 0, 0.f, 1, 1}, {0, p.M, (int)(p.g_term_bytes * P4V_TILE), 0, 0.f, 0.f, 0.f, 0, 0.f, 2, 1}};
+    P4V_CUDA_OK(cudaMemcpyAsync(at<void>(ws, p.o_segsG), sg, sizeof(sg), cudaMemcpyHostToDevice, st));
+  }
   return 0;
 }
 
@@ -407,6 +463,80 @@ int search_step(const LinPlan& p, void* ws, StepRef cur, const StepRef* next, bo
   return p4v_commit_step(c, st);
 }
 
+// Whole W search of one round in normal-equation form (gram.cu): residual once, then per column block
+// update pass -> pair image -> Gram GEMM (the sweep kernel in output mode) -> candidate evaluation -> select -> commit.
+int gram_wsearch(const LinPlan& p, void* ws, const float* x, const float* W, const float* bias, const float* y, const float* g,
+                 int h_begin, int h_end, float* score_log, cudaStream_t st) {
+  int rc;
+  const float w_lo = (float)-p.w_qmax, w_hi = (float)(p.w_qmax - 1);
+  // e = y - yhat(current step sizes), exact integer products (every segment as a fixed group)
+  if ((rc = tables_for(p, ws, p.fwd, -1, 0, st))) return rc;
+  {
+    SweepParams sp; fill_sweep(p, ws, p.fwd, sp);
+    sp.Y = y; sp.Gr = g; sp.bias = p.d.has_bias ? bias : nullptr;
+    sp.out = at<float>(ws, p.o_E); sp.out_residual = 1; sp.n_cand = 1; sp.order = 0; sp.R_cand = nullptr; sp.C_cand = nullptr;
+    if ((rc = run_sweep(p, p.fwd, sp, st))) return rc;
+  }
+  if ((rc = p4v_xq_transpose(x, p.M, p.K, p.g_Mp, at<float>(ws, p.o_dX), p.crb_acts, (float)-p.a_qmax, (float)(p.a_qmax - 1),
+                             at<int8_t>(ws, p.o_XqT), st))) return rc;
+  const unsigned long long tile_bytes = (unsigned long long)P4V_TILE * 2 * p.g_term_bytes;
+  for (int h = h_begin; h < h_end; ++h) {
+    GramUpdateArgs u{};
+    u.E = at<float>(ws, p.o_E); u.G = g; u.gscale = at<float>(ws, p.o_gscale);
+    u.W = W; u.M = p.M; u.O = p.O; u.K = p.K; u.XqT = at<int8_t>(ws, p.o_XqT); u.Mp = p.g_Mp;
+    u.dX = at<float>(ws, p.o_dX); u.crb_acts = p.crb_acts;
+    u.dW = at<float>(ws, p.o_dW); u.dW_prev = at<float>(ws, p.o_dprev); u.n_V = p.d.n_V; u.n_H = p.d.n_H; u.crb_rows = p.crb_rows;
+    u.h_prev = h > h_begin ? h - 1 : -1; u.k_prev = (h - 1) * p.g_ks; u.k_next = h * p.g_ks; u.ks = p.g_ks;
+    u.w_lo = w_lo; u.w_hi = w_hi; u.Upart = at<float>(ws, p.o_Upart); u.E2part = at<float>(ws, p.o_E2part);
+    if ((rc = p4v_gram_update(u, st))) return rc;
+    if ((rc = p4v_pair_image(at<int8_t>(ws, p.o_XqT), p.g_Mp, p.M, h * p.g_ks, p.g_ks, p.g_npairs, p.g_tiles_p, tile_bytes,
+                             p.g_term_bytes, at<uint8_t>(ws, p.o_Z), st))) return rc;
+    {
+      SweepParams sp{};
+      sp.R_cur = at<uint8_t>(ws, p.o_G2T); sp.C_cur = at<uint8_t>(ws, p.o_Z);
+      sp.R_tile_bytes = sp.C_tile_bytes = tile_bytes;
+      sp.P = 1; sp.M = p.O; sp.N = p.g_ldH; sp.tiles_m = p.tiles_o; sp.tiles_n = p.g_tiles_p;
+      sp.ld = p.g_ldH; sp.prob_stride = 0; sp.gscale = at<float>(ws, p.o_gscale);
+      sp.jobs = at<P4VJob>(ws, p.o_gjobs); sp.n_fixed_jobs = (int)p.gjobs.size(); sp.n_fixed_groups = 3;
+      sp.fix_scale = at<float>(ws, p.o_ones); sp.candA = sp.fix_scale; sp.candB = sp.fix_scale;
+      sp.nsg = p.g_tiles_p * P4V_TILE_CG; sp.sg_mode = P4V_SG_COLUMN;
+      sp.n_cand = 1; sp.out = at<float>(ws, p.o_H); sp.order = 0; sp.is_int8 = 0;
+      if ((rc = p4v_run_sweep(sp, p.gjobs.data(), p.d.kernel, st))) return rc;
+    }
+    GramEvalArgs ev{};
+    ev.H = at<float>(ws, p.o_H); ev.ldH = p.g_ldH; ev.npairs = p.g_npairs;
+    if ((rc = p4v_gram_reduce(u.Upart, u.E2part, p.g_nmblk, p.O, p.g_ks, at<float>(ws, p.o_U), at<float>(ws, p.o_E2), st))) return rc;
+    ev.U = at<float>(ws, p.o_U); ev.E2 = at<float>(ws, p.o_E2);
+    ev.W = W; ev.O = p.O; ev.K = p.K; ev.k_first = h * p.g_ks; ev.ks = p.g_ks;
+    ev.dW = at<float>(ws, p.o_dW); ev.dW0 = at<float>(ws, p.o_dW0); ev.n_H = p.d.n_H; ev.h = h;
+    ev.dX = at<float>(ws, p.o_dX); ev.crb_acts = p.crb_acts;
+    ev.factors = at<float>(ws, p.o_factors); ev.n_cand = p.d.eq_n;
+    ev.n_groups = p.d.n_V; ev.rows_per_group = p.crb_rows; ev.osplit = p.g_osplit; ev.rows_per_block = p.g_opb;
+    ev.w_lo = w_lo; ev.w_hi = w_hi;
+    ev.sums = at<double>(ws, p.o_scores) + (size_t)p.d.eq_n * p.d.n_V; ev.n_keys = p.d.n_V * p.g_osplit;
+    ev.sums2 = at<double>(ws, p.o_scores);
+    if ((rc = p4v_gram_eval(ev, st))) return rc;
+    SelectArgs f{};
+    f.sums = ev.sums2; f.n_cand = p.d.eq_n; f.n_keys = p.d.n_V; f.n_groups = p.d.n_V; f.keys_per_group = 1;
+    f.inv_count = 1.0 / ((double)p.d.tokens * (double)p.crb_rows);
+    f.gscale = at<float>(ws, p.o_gscale); f.factors = at<float>(ws, p.o_factors);
+    f.d0 = at<float>(ws, p.o_dW0); f.d = at<float>(ws, p.o_dW); f.d_stride = p.d.n_H; f.d_col = h;
+    f.best = at<int>(ws, p.o_best); f.score_log = score_log; f.d_prev = at<float>(ws, p.o_dprev); f.has_next = 0;
+    if ((rc = p4v_select_step(f, st))) return rc;
+    const Step& s = p.wsteps[h];
+    CommitArgs c{};
+    c.best = f.best; c.n_groups = p.d.n_V;
+    c.cand = at<uint8_t>(ws, p.o_Wcand); c.cand_tile_bytes = (unsigned long long)P4V_TILE * p.KB_W;
+    c.cand_plane_stride = c.cand_tile_bytes * p.tiles_o;
+    c.cur = at<uint8_t>(ws, p.o_Wcur); c.cur_tile_bytes = c.cand_tile_bytes;
+    c.P = 1; c.tiles = p.tiles_o; c.rows_per_group = p.crb_rows; c.problem_groups = 0;
+    c.segs = at<CommitSeg>(ws, p.o_commits) + s.commit_off; c.nseg = s.ncommit; c.commit_chunks = s.commit_chunks;
+    if ((rc = p4v_commit_step(c, st))) return rc;
+    if (score_log) score_log += (size_t)p.d.eq_n * p.d.n_V;
+  }
+  return 0;
+}
+
 int begin_impl(const LinPlan& p, const float* x, const float* W, const float* g, void* ws, cudaStream_t st) {
   int rc;
   if ((rc = upload_tables(p, ws, st))) return rc;
@@ -419,6 +549,15 @@ int begin_impl(const LinPlan& p, const float* x, const float* W, const float* g,
   if ((rc = p4v_keys_to_delta(keys, nW, (float)p.w_qmax - 0.5f, at<float>(ws, p.o_dW0), at<float>(ws, p.o_dW), st))) return rc;
   if ((rc = p4v_keys_to_delta(keys + nW, p.d.n_a, (float)p.a_qmax - 0.5f, at<float>(ws, p.o_dX0), at<float>(ws, p.o_dX), st))) return rc;
   if ((rc = p4v_make_gscale(keys + nW + p.d.n_a, at<float>(ws, p.o_gscale), st))) return rc;
+  if (p.gram) {          // (gs*g)^2 as two exact bf16 terms, transposed: rows = output channels, K = tokens
+    QuantImageArgs q{};
+    q.src = g; q.ld = p.O; q.prob_stride = 0; q.src_transposed = 1;
+    q.P = 1; q.rows = p.O; q.tiles = p.tiles_o;
+    q.dst = at<uint8_t>(ws, p.o_G2T); q.tile_bytes = (unsigned long long)P4V_TILE * 2 * p.g_term_bytes; q.plane_stride = 0;
+    q.n_planes = 1; q.factors = nullptr; q.delta = at<float>(ws, p.o_dW0); q.rows_per_block = p.O + P4V_TILE; q.d_stride = 0; q.d_mod = 1;
+    q.segs = at<P4VSeg>(ws, p.o_segsG); q.nseg = 2; q.is_int8 = 0; q.presc = at<float>(ws, p.o_gscale);
+    if ((rc = p4v_quant_image(q, st))) return rc;
+  }
   if ((rc = quant_W(p, ws, W, at<float>(ws, p.o_dW0), false, st))) return rc;
   if ((rc = quant_W(p, ws, W, at<float>(ws, p.o_dW0), true, st))) return rc;
   if ((rc = quant_X(p, ws, x, at<float>(ws, p.o_dX0), false, st))) return rc;
@@ -501,15 +640,28 @@ extern "C" int p4v_linear_calibrate(const p4v_linear_desc* d, const float* x, co
   P4V_REQUIRE(workspace_bytes >= p.total, "linear_calibrate: workspace too small (%zu < %zu)", workspace_bytes, p.total);
   cudaStream_t st = (cudaStream_t)stream;
   if ((rc = begin_impl(p, x, weight, raw_grad, workspace, st))) return rc;
-  std::vector<StepRef> seq;
-  for (int e = 0; e < d->search_round; ++e) {
-    for (int h = 0; h < d->n_H; ++h) seq.push_back(StepRef{true, h});
-    for (int a = 0; a < d->n_a; ++a) seq.push_back(StepRef{false, a});
-  }
-  for (size_t i = 0; i < seq.size(); ++i) {
-    if ((rc = search_step(p, workspace, seq[i], i + 1 < seq.size() ? &seq[i + 1] : nullptr, i > 0, bias, raw_out, raw_grad,
-                          score_log, st))) return rc;
-    if (score_log) score_log += seq[i].is_w ? (size_t)d->eq_n * d->n_V : (size_t)d->eq_n;
+  if (p.gram) {
+    for (int e = 0; e < d->search_round; ++e) {
+      if ((rc = gram_wsearch(p, workspace, x, weight, bias, raw_out, raw_grad, 0, d->n_H, score_log, st))) return rc;
+      if (score_log) score_log += (size_t)d->n_H * d->eq_n * d->n_V;
+      for (int a = 0; a < d->n_a; ++a) {
+        StepRef nx{false, a + 1};
+        if ((rc = search_step(p, workspace, StepRef{false, a}, a + 1 < d->n_a ? &nx : nullptr, a > 0, bias, raw_out, raw_grad,
+                              score_log, st))) return rc;
+        if (score_log) score_log += d->eq_n;
+      }
+    }
+  } else {
+    std::vector<StepRef> seq;
+    for (int e = 0; e < d->search_round; ++e) {
+      for (int h = 0; h < d->n_H; ++h) seq.push_back(StepRef{true, h});
+      for (int a = 0; a < d->n_a; ++a) seq.push_back(StepRef{false, a});
+    }
+    for (size_t i = 0; i < seq.size(); ++i) {
+      if ((rc = search_step(p, workspace, seq[i], i + 1 < seq.size() ? &seq[i + 1] : nullptr, i > 0, bias, raw_out, raw_grad,
+                            score_log, st))) return rc;
+      if (score_log) score_log += seq[i].is_w ? (size_t)d->eq_n * d->n_V : (size_t)d->eq_n;
+    }
   }
   P4V_CUDA_OK(cudaMemcpyAsync(w_interval, at<float>(workspace, p.o_dW), (size_t)d->n_V * d->n_H * 4, cudaMemcpyDeviceToDevice, st));
   P4V_CUDA_OK(cudaMemcpyAsync(a_interval, at<float>(workspace, p.o_dX), (size_t)d->n_a * 4, cudaMemcpyDeviceToDevice, st));

@@ -139,7 +139,8 @@ __global__ void quant_image_kernel(const QuantImageArgs a, int chunks_total) {
       const int kk = chunk * epc + e;
       float q = 0.f;
       if (kk < sg.klen) {
-        const float v = vals[e];
+        float v = vals[e];
+        if (sg.square) { if (a.presc) v *= a.presc[0]; v = v * v; }
         if (sg.split3) {
           const float b1 = __bfloat162float(__float2bfloat16_rn(v));
           const float b2 = __bfloat162float(__float2bfloat16_rn(v - b1));
@@ -262,6 +263,7 @@ __global__ void __launch_bounds__(1024) select_step_kernel(const SelectArgs a) {
     }
     if (lane == 0) {
       const size_t di = (size_t)g * a.d_stride + a.d_col;
+      if (a.d_prev) a.d_prev[g] = a.d[di];
       a.d[di] = a.factors[bi] * a.d0[di];
       a.best[g] = bi;
     }

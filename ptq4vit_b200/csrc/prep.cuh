@@ -13,6 +13,7 @@ struct P4VSeg {          // one K segment of an operand image
   int sos_part;          // split-of-softmax twin quantizer (matmul.py:595-598): 1 = high part, 2 = low part, 0 = plain
   float qm1;             // qmax - 1 for the sos parts
   int split3;            // 1..3: no quantisation, emit the i-th bf16 term of the exact 3-way split of the fp32 value
+  int square;            // with split3: split v*v*presc^2 instead of v (Gram operand g^2)
 };
 
 struct QuantImageArgs {
@@ -28,6 +29,7 @@ struct QuantImageArgs {
   const P4VSeg* segs; int nseg;
   int is_int8;
   const float* split;    // sos: device scalar split point for the current image (candidate planes use factors[plane])
+  const float* presc;    // optional device scalar multiplied into the source before `square`
 };
 int p4v_quant_image(const QuantImageArgs& a, cudaStream_t st);
 
@@ -76,6 +78,7 @@ struct SelectArgs {
   const float* d0; float* d; int d_stride, d_col;    // d[g * d_stride + d_col] = fl(f[best_g] * d0[...])
   int* best;                                         // [n_groups]
   float* score_log;                                  // [n_cand][n_groups] fp32 (optional)
+  float* d_prev;                                     // optional [n_groups]: the step sizes before this step
   int has_next; StepTablesArgs next;
 };
 int p4v_select_step(const SelectArgs& a, cudaStream_t st);

@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(256) sweep_simt_kernel(const __grid_constant__
       const int gm = tm * P4V_TILE + row;
       if (gm >= P.M || gcol >= P.N) continue;
       const size_t off = (size_t)p * P.prob_stride + (size_t)gm * P.ld + gcol;
-      float r = (P.out ? 0.f : P.Y[off]) - (P.bias ? P.bias[gcol] : 0.f);
+      float r = ((P.out && !P.out_residual) ? 0.f : P.Y[off]) - (P.bias ? P.bias[gcol] : 0.f);
       const float g = P.out ? 0.f : P.Gr[off] * gs;
       // fixed groups
       float acc = 0.f;
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256) sweep_simt_kernel(const __grid_constant__
         acc += dot_job<kInt8>(Rcur + jb.r_off, Ccur + jb.c_off, row, col, jb.kb);
         if (jb.flags & P4V_JOB_LAST) r = fmaf(-P.fix_scale[(size_t)jb.group * P.nsg + sg], acc, r);
       }
-      if (P.out) { P.out[off] = -r; continue; }
+      if (P.out) { P.out[off] = P.out_residual ? r : -r; continue; }
       for (int j = 0; j < P.n_cand_jobs; ++j) {
         const P4VJob jb = P.jobs[P.n_fixed_jobs + j];
         if (jb.flags & P4V_JOB_FIRST) acc = 0.f;

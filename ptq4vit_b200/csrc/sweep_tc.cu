@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const uint32_t tbase = tmem + lane_addr + kAccBase + hf * 64;       // this thread's columns of slot 0
     const uint32_t tstore = tmem + lane_addr + hf * 64;                 // parked residual target (!kSingle)
-    const float gs = P.out ? 1.f : *P.gscale;
+    const float gs = (P.out && !P.out_residual) ? 1.f : *P.gscale;
     AccRing ring{0u, 0u, kSlots};
     float r[64], g[64];
     uint32_t a0[32], a1[32];
@@ -482,7 +482,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
         const float* yrow = P.Y + (size_t)f.p * P.prob_stride + (size_t)gm * P.ld;
         const float* grow = P.Gr + (size_t)f.p * P.prob_stride + (size_t)gm * P.ld;
         const bool row_ok = gm < P.M;
-        if (P.out != nullptr) {           // quant_forward: r starts at -bias, output = -r
+        if (P.out != nullptr && !P.out_residual) {           // quant_forward: r starts at -bias, output = -r
 #pragma unroll
           for (int j = 0; j < 64; ++j) {
             const int col = col0 + j;
@@ -525,7 +525,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
         if (gm < P.M) {
           float* orow = P.out + (size_t)f.p * P.prob_stride + (size_t)gm * P.ld;
 #pragma unroll
-          for (int j = 0; j < 64; ++j) if (col0 + j < P.N) orow[col0 + j] = -r[j];
+          for (int j = 0; j < 64; ++j) if (col0 + j < P.N) orow[col0 + j] = P.out_residual ? r[j] : -r[j];
         }
         continue;
       }
