@@ -77,13 +77,14 @@ __global__ void pair_image_kernel(const int8_t* __restrict__ XqT, int Mp, int M,
 }
 
 // One pass over e and g: apply the rank-ks update of the previous step, accumulate U and sum (g e)^2 for the next slab.
-// block = 128 output channels x GRAM_BM tokens; thread = one output channel.
+// block = 256 output channels x GRAM_BM tokens; thread = TWO output channels (o, o+128): every xhat value fetched from
+// shared memory feeds two FMAs, which halves the shared-memory traffic that otherwise bounds this kernel.
 template <int KS>
 __global__ void __launch_bounds__(128) gram_update_kernel(const GramUpdateArgs a) {
   extern __shared__ float sm[];
   float* xp = sm;                       // [BM][KS] previous slab (xhat), only if a.h_prev >= 0
   float* xn = sm + GRAM_BM * KS;        // [BM][KS] next slab
-  const int o = blockIdx.x * 128 + threadIdx.x;
+  const int oA = blockIdx.x * 256 + threadIdx.x, oB = oA + 128;
   const int m0 = blockIdx.y * GRAM_BM;
   const int rows = min(GRAM_BM, a.M - m0);
   const float gs = a.gscale[0];
@@ -113,62 +114,82 @@ __global__ void __launch_bounds__(128) gram_update_kernel(const GramUpdateArgs a
 #pragma unroll
     for (int e = 0; e < 16; ++e) { xn[(mm0 + e) * KS + k] = vn[e]; xp[(mm0 + e) * KS + k] = vp[e]; }
   }
-  float delta[KS], acc[KS];
+  float dA[KS], dB[KS], accA[KS], accB[KS];
 #pragma unroll
-  for (int k = 0; k < KS; ++k) { delta[k] = 0.f; acc[k] = 0.f; }
-  if (has_prev && o < a.O) {
-    const int v = min(o / a.crb_rows, a.n_V - 1);
-    const float d_new = a.dW[v * a.n_H + a.h_prev], d_old = a.dW_prev[v];
-    const float* wrow = a.W + (size_t)o * a.K + a.k_prev;
+  for (int k = 0; k < KS; ++k) { dA[k] = 0.f; dB[k] = 0.f; accA[k] = 0.f; accB[k] = 0.f; }
+  const bool okA = oA < a.O, okB = oB < a.O;
+  if (has_prev) {
 #pragma unroll
-    for (int k = 0; k < KS; ++k)
-      if (k < a.ks) delta[k] = fq_dev(wrow[k], d_new, a.w_lo, a.w_hi) - fq_dev(wrow[k], d_old, a.w_lo, a.w_hi);
+    for (int half = 0; half < 2; ++half) {
+      const int o = half ? oB : oA;
+      if (o < a.O) {
+        const int v = min(o / a.crb_rows, a.n_V - 1);
+        const float d_new = a.dW[v * a.n_H + a.h_prev], d_old = a.dW_prev[v];
+        const float* wrow = a.W + (size_t)o * a.K + a.k_prev;
+#pragma unroll
+        for (int k = 0; k < KS; ++k)
+          if (k < a.ks) {
+            const float dl = fq_dev(wrow[k], d_new, a.w_lo, a.w_hi) - fq_dev(wrow[k], d_old, a.w_lo, a.w_hi);
+            if (half) dB[k] = dl; else dA[k] = dl;
+          }
+      }
+    }
   }
   __syncthreads();
-  float e2 = 0.f;
-  if (o < a.O) {
-    constexpr int UN = 16;                                  // tokens in flight per thread (hides the HBM latency)
-    for (int mm0 = 0; mm0 < rows; mm0 += UN) {
-      float ev[UN], gv[UN];
+  float e2A = 0.f, e2B = 0.f;
+  constexpr int UN = 4;                                   // tokens in flight per thread and channel
+  for (int mm0 = 0; mm0 < rows; mm0 += UN) {
+    float eA[UN], gA[UN], eB[UN], gB[UN];
 #pragma unroll
-      for (int u = 0; u < UN; ++u) {
-        const bool ok = mm0 + u < rows;
-        const size_t off = (size_t)(m0 + mm0 + u) * a.O + o;
-        ev[u] = ok ? a.E[off] : 0.f;
-        gv[u] = ok ? a.G[off] * gs : 0.f;
-      }
+    for (int u = 0; u < UN; ++u) {
+      const bool ok = mm0 + u < rows;
+      const size_t off = (size_t)(m0 + mm0 + u) * a.O;
+      eA[u] = (ok && okA) ? a.E[off + oA] : 0.f; gA[u] = (ok && okA) ? a.G[off + oA] * gs : 0.f;
+      eB[u] = (ok && okB) ? a.E[off + oB] : 0.f; gB[u] = (ok && okB) ? a.G[off + oB] * gs : 0.f;
+    }
 #pragma unroll
-      for (int u = 0; u < UN; ++u) {
-        const int mm = mm0 + u;
-        if (mm < rows) {
-          float e = ev[u];
-          if (has_prev) {
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;      // four independent chains
-#pragma unroll
-            for (int k = 0; k < KS; k += 4) {
-              const float4 xv = *reinterpret_cast<const float4*>(&xp[mm * KS + k]);
-              s0 = fmaf(xv.x, delta[k], s0); s1 = fmaf(xv.y, delta[k + 1], s1);
-              s2 = fmaf(xv.z, delta[k + 2], s2); s3 = fmaf(xv.w, delta[k + 3], s3);
-            }
-            e -= (s0 + s1) + (s2 + s3);
-            a.E[(size_t)(m0 + mm) * a.O + o] = e;
-          }
-          const float ge = gv[u] * e;
-          e2 = fmaf(ge, ge, e2);
-          const float w = gv[u] * ge;
+    for (int u = 0; u < UN; ++u) {
+      const int mm = mm0 + u;
+      if (mm < rows) {
+        float ea = eA[u], eb = eB[u];
+        if (has_prev) {
+          float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
 #pragma unroll
           for (int k = 0; k < KS; k += 4) {
-            const float4 xv = *reinterpret_cast<const float4*>(&xn[mm * KS + k]);
-            acc[k] = fmaf(w, xv.x, acc[k]); acc[k + 1] = fmaf(w, xv.y, acc[k + 1]);
-            acc[k + 2] = fmaf(w, xv.z, acc[k + 2]); acc[k + 3] = fmaf(w, xv.w, acc[k + 3]);
+            const float4 xv = *reinterpret_cast<const float4*>(&xp[mm * KS + k]);
+            a0 = fmaf(xv.x, dA[k], a0); a1 = fmaf(xv.y, dA[k + 1], a1); a0 = fmaf(xv.z, dA[k + 2], a0); a1 = fmaf(xv.w, dA[k + 3], a1);
+            b0 = fmaf(xv.x, dB[k], b0); b1 = fmaf(xv.y, dB[k + 1], b1); b0 = fmaf(xv.z, dB[k + 2], b0); b1 = fmaf(xv.w, dB[k + 3], b1);
           }
+          ea -= a0 + a1; eb -= b0 + b1;
+          const size_t off = (size_t)(m0 + mm) * a.O;
+          if (okA) a.E[off + oA] = ea;
+          if (okB) a.E[off + oB] = eb;
+        }
+        const float geA = gA[u] * ea, geB = gB[u] * eb;
+        e2A = fmaf(geA, geA, e2A); e2B = fmaf(geB, geB, e2B);
+        const float wA = gA[u] * geA, wB = gB[u] * geB;
+#pragma unroll
+        for (int k = 0; k < KS; k += 4) {
+          const float4 xv = *reinterpret_cast<const float4*>(&xn[mm * KS + k]);
+          accA[k] = fmaf(wA, xv.x, accA[k]); accA[k + 1] = fmaf(wA, xv.y, accA[k + 1]);
+          accA[k + 2] = fmaf(wA, xv.z, accA[k + 2]); accA[k + 3] = fmaf(wA, xv.w, accA[k + 3]);
+          accB[k] = fmaf(wB, xv.x, accB[k]); accB[k + 1] = fmaf(wB, xv.y, accB[k + 1]);
+          accB[k + 2] = fmaf(wB, xv.z, accB[k + 2]); accB[k + 3] = fmaf(wB, xv.w, accB[k + 3]);
         }
       }
     }
-    float* up = a.Upart + ((size_t)blockIdx.y * a.O + o) * a.ks;
+  }
+  if (okA) {
+    float* up = a.Upart + ((size_t)blockIdx.y * a.O + oA) * a.ks;
 #pragma unroll
-    for (int k = 0; k < KS; ++k) if (k < a.ks) up[k] = acc[k];
-    a.E2part[(size_t)blockIdx.y * a.O + o] = e2;
+    for (int k = 0; k < KS; ++k) if (k < a.ks) up[k] = accA[k];
+    a.E2part[(size_t)blockIdx.y * a.O + oA] = e2A;
+  }
+  if (okB) {
+    float* up = a.Upart + ((size_t)blockIdx.y * a.O + oB) * a.ks;
+#pragma unroll
+    for (int k = 0; k < KS; ++k) if (k < a.ks) up[k] = accB[k];
+    a.E2part[(size_t)blockIdx.y * a.O + oB] = e2B;
   }
 }
 
@@ -274,7 +295,7 @@ int p4v_pair_image(const int8_t* XqT, int Mp, int M, int k_first, int ks, int np
 }
 
 template <int KS> static int launch_update(const GramUpdateArgs& a, cudaStream_t st) {
-  dim3 grid(p4v_cdiv(a.O, 128), p4v_cdiv(a.M, GRAM_BM));
+  dim3 grid(p4v_cdiv(a.O, 256), p4v_cdiv(a.M, GRAM_BM));
   const size_t smem = (size_t)2 * GRAM_BM * KS * sizeof(float);
   P4V_CUDA_OK(cudaFuncSetAttribute(gram_update_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   gram_update_kernel<KS><<<grid, 128, smem, st>>>(a); p4v_count_launch();

@@ -72,12 +72,30 @@ __device__ __forceinline__ bool mbar_try(uint32_t addr, uint32_t parity) {
   __trap();
   while (true) {}
 }
-__device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {
+__device__ __noinline__ void mbar_wait_slow(uint32_t addr, uint32_t parity) {
+  const long long t0 = clock64();
+  while (!mbar_try(addr, parity))
+    if (clock64() - t0 > 4000000000ll) mbar_timeout(addr, parity);
+}
+__device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {     // fully inline: safe with many live registers
   const uint32_t addr = smem_u32(bar);
   if (mbar_try(addr, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try(addr, parity))
     if (clock64() - t0 > 4000000000ll) mbar_timeout(addr, parity);
+}
+__device__ __forceinline__ void mbar_wait_addr(uint32_t addr, uint32_t parity) {
+  if (!mbar_try(addr, parity)) mbar_wait_slow(addr, parity);
+}
+__device__ __forceinline__ void mbar_expect_tx_addr(uint32_t addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_addr(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_commit_addr(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, void* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -101,6 +119,11 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   constexpr uint64_t lbo = (P4V_TILE * 16) >> 4;   // 2048 B
   constexpr uint64_t sbo = 128 >> 4;               // 128 B
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | (lbo << 16) | (sbo << 32) | (1ull << 46);
+}
+// descriptor with the constant fields only; the 14-bit start-address field (bits 0..13, units of 16 B) is added per use
+__device__ __forceinline__ uint64_t desc_hi_const() {
+  constexpr uint64_t lbo = (P4V_TILE * 16) >> 4, sbo = 128 >> 4;
+  return (lbo << 16) | (sbo << 32) | (1ull << 46);
 }
 template <bool kInt8>
 __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t accumulate) {
@@ -127,6 +150,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
         "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
         "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld32f(uint32_t taddr, float* v) {   // same, straight into a float register array
@@ -202,36 +233,36 @@ __device__ __forceinline__ void unpack2(f32x2 v, float& a, float& b) { asm("mov.
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 
-// Half an accumulator (32 of this thread's 64 columns, already in registers) against the running residual.
+// A quarter of this thread's 64 accumulator columns (16 columns = one scale / score group, already in registers)
+// against the running residual.
 //   kScore == false:  r -= s * acc                        (fixed segments / non-final candidate segments)
-//   kScore == true :  p = sum (g * (r - s*acc))^2 per 16 columns   (final candidate segment; r is not modified)
+//   kScore == true :  p = sum (g * (r - s*acc))^2          (final candidate segment; r is not modified)
 template <bool kInt8, bool kScore, bool kPacked, int OFF>
-__device__ __forceinline__ void consume_chunk(const uint32_t (&a)[32], float (&r)[64], const float (&g)[64],
-                                              const float s_lo, const float s_hi, float& p_lo, float& p_hi) {
+__device__ __forceinline__ void consume16(const uint32_t (&a)[16], float (&r)[64], const float (&g)[64], const float s, float& p) {
   if constexpr (kPacked) {
-    f32x2 q_lo = 0ull, q_hi = 0ull;
-    const f32x2 ns_lo = pack2(-s_lo, -s_lo), ns_hi = pack2(-s_hi, -s_hi);
+    f32x2 q0 = 0ull, q1 = 0ull;
+    const f32x2 ns = pack2(-s, -s);
 #pragma unroll
-    for (int j = 0; j < 32; j += 2) {
+    for (int j = 0; j < 16; j += 2) {
       const f32x2 f = pack2(acc_to_float<kInt8>(a[j]), acc_to_float<kInt8>(a[j + 1]));
-      const f32x2 d = fma2(j < 16 ? ns_lo : ns_hi, f, pack2(r[OFF + j], r[OFF + j + 1]));
+      const f32x2 d = fma2(ns, f, pack2(r[OFF + j], r[OFF + j + 1]));
       if constexpr (kScore) {
         const f32x2 w = mul2(pack2(g[OFF + j], g[OFF + j + 1]), d);
-        if (j < 16) q_lo = fma2(w, w, q_lo); else q_hi = fma2(w, w, q_hi);
+        if (j & 2) q1 = fma2(w, w, q1); else q0 = fma2(w, w, q0);
       } else {
         unpack2(d, r[OFF + j], r[OFF + j + 1]);
       }
     }
-    if constexpr (kScore) { float x, y; unpack2(q_lo, x, y); p_lo = x + y; unpack2(q_hi, x, y); p_hi = x + y; }
+    if constexpr (kScore) { float x0, y0, x1, y1; unpack2(q0, x0, y0); unpack2(q1, x1, y1); p = (x0 + y0) + (x1 + y1); }
   } else {
-    float q_lo = 0.f, q_hi = 0.f;
+    float q0 = 0.f, q1 = 0.f;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float d = fmaf(-(j < 16 ? s_lo : s_hi), acc_to_float<kInt8>(a[j]), r[OFF + j]);
-      if constexpr (kScore) { const float w = g[OFF + j] * d; if (j < 16) q_lo = fmaf(w, w, q_lo); else q_hi = fmaf(w, w, q_hi); }
+    for (int j = 0; j < 16; ++j) {
+      const float d = fmaf(-s, acc_to_float<kInt8>(a[j]), r[OFF + j]);
+      if constexpr (kScore) { const float w = g[OFF + j] * d; if (j & 1) q1 = fmaf(w, w, q1); else q0 = fmaf(w, w, q0); }
       else r[OFF + j] = d;
     }
-    if constexpr (kScore) { p_lo = q_lo; p_hi = q_hi; }
+    if constexpr (kScore) p = q0 + q1;
   }
 }
 
@@ -289,19 +320,28 @@ __device__ __forceinline__ float reduce4_over_rows(float v0, float v1, float v2,
 // half has landed in registers.
 struct AccRing { uint32_t slot, phase, nslots; };
 
-__device__ __forceinline__ void acc_begin(SmemCtl& S, AccRing& ring, uint32_t tbase, uint32_t (&a0)[32]) {
+__device__ __forceinline__ void acc_begin(SmemCtl& S, AccRing& ring, uint32_t tbase, uint32_t (&a0)[16]) {
   mbar_wait(&S.acc_full[ring.slot], ring.phase);
   tc_fence_after();
-  tmem_ld32(tbase + ring.slot * kAccCols, a0);
+  tmem_ld16(tbase + ring.slot * kAccCols, a0);
   tmem_wait_ld();
 }
 
+// One accumulator = four 16-column quarters, double buffered in a0/a1: the TMEM load of the next quarter is in flight
+// while the CUDA cores work on the current one; the slot returns to the MMA warp once its last quarter is in registers.
 template <bool kInt8, bool kScore, bool kPacked>
-__device__ __forceinline__ void acc_step(SmemCtl& S, AccRing& ring, uint32_t tbase, int lane, uint32_t (&a0)[32],
-                                         uint32_t (&a1)[32], float (&r)[64], const float (&g)[64], const float4 sc,
+__device__ __forceinline__ void acc_step(SmemCtl& S, AccRing& ring, uint32_t tbase, int lane, uint32_t (&a0)[16],
+                                         uint32_t (&a1)[16], float (&r)[64], const float (&g)[64], const float4 sc,
                                          float (&p)[4], const bool has_next) {
-  tmem_ld32(tbase + ring.slot * kAccCols + 32, a1);
-  consume_chunk<kInt8, kScore, kPacked, 0>(a0, r, g, sc.x, sc.y, p[0], p[1]);
+  const uint32_t t0 = tbase + ring.slot * kAccCols;
+  tmem_ld16(t0 + 16, a1);
+  consume16<kInt8, kScore, kPacked, 0>(a0, r, g, sc.x, p[0]);
+  tmem_wait_ld();
+  tmem_ld16(t0 + 32, a0);
+  consume16<kInt8, kScore, kPacked, 16>(a1, r, g, sc.y, p[1]);
+  tmem_wait_ld();
+  tmem_ld16(t0 + 48, a1);
+  consume16<kInt8, kScore, kPacked, 32>(a0, r, g, sc.z, p[2]);
   tmem_wait_ld();
   tc_fence_before();
   __syncwarp();
@@ -310,9 +350,9 @@ __device__ __forceinline__ void acc_step(SmemCtl& S, AccRing& ring, uint32_t tba
   if (has_next) {
     mbar_wait(&S.acc_full[ring.slot], ring.phase);
     tc_fence_after();
-    tmem_ld32(tbase + ring.slot * kAccCols, a0);
+    tmem_ld16(tbase + ring.slot * kAccCols, a0);
   }
-  consume_chunk<kInt8, kScore, kPacked, 32>(a1, r, g, sc.z, sc.w, p[2], p[3]);
+  consume16<kInt8, kScore, kPacked, 48>(a1, r, g, sc.w, p[3]);
   if (has_next) tmem_wait_ld();
 }
 
@@ -353,14 +393,15 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
   asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == 0) {
     // ======================= TMA producer (whole warp runs the loop, one elected lane issues) =======================
+    // Single-warp loop: every instruction is on the critical path of a ~100-instruction-per-job budget, so addresses
+    // are advanced incrementally and barrier / stage addresses are plain 32-bit shared-memory offsets.
     {
       uint32_t stage = 0, phase = 0, rbuf = 0, rphase = 0;
+      const uint32_t full0 = smem_u32(&S.full[0]), empty0 = smem_u32(&S.empty[0]);
       while (next_frag(P, sched, f)) {
         const size_t rt = (size_t)(f.p * P.tiles_m + f.tm), ct = (size_t)(f.p * P.tiles_n + f.tn);
         const uint8_t* r_cur = P.R_cur + rt * P.R_tile_bytes;
         const uint8_t* c_cur = P.C_cur + ct * P.C_tile_bytes;
-        const uint8_t* r_cand = P.R_cand + rt * P.R_cand_tile_bytes;
-        const uint8_t* c_cand = P.C_cand + ct * P.C_cand_tile_bytes;
         if (resB) {      // row operand of the candidate jobs: once per fragment, reused by every candidate
           mbar_wait(&S.res_empty[rbuf], rphase ^ 1);
           uint32_t total = 0;
@@ -372,30 +413,40 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
               bulk_g2s(resR + rbuf * resB + jb.res_off, r_cur + jb.r_off, (uint32_t)jb.kb * P4V_TILE, &S.res_full[rbuf]);
             }
           }
-          __syncwarp();
           if (++rbuf == 2) { rbuf = 0; rphase ^= 1; }
         }
-        const int n_issue = P.n_fixed_jobs + (f.c1 - f.c0) * P.n_cand_jobs;
-        int jidx = 0, c = f.c0;
-        for (int it = 0; it < n_issue; ++it) {
-          const bool is_fixed = it < P.n_fixed_jobs;
-          const P4VJob j = S.jobs[is_fixed ? it : P.n_fixed_jobs + jidx];
-          mbar_wait(&S.empty[stage], phase ^ 1);
+        auto issue = [&](const P4VJob j, const uint8_t* rr, const uint8_t* cc) {
+          mbar_wait_addr(empty0 + stage * 8, phase ^ 1);
           const uint32_t bytes = (uint32_t)j.kb * P4V_TILE;
-          const uint8_t* cc = ((j.flags & P4V_JOB_CCAND) ? c_cand + (size_t)c * P.C_cand_stride : c_cur) + j.c_off;
-          const uint8_t* rr = ((j.flags & P4V_JOB_RCAND) ? r_cand + (size_t)c * P.R_cand_stride : r_cur) + j.r_off;
           if (elect_one()) {
+            const uint32_t fb = full0 + stage * 8;
             if (j.flags & P4V_JOB_RRES) {
-              mbar_expect_tx(&S.full[stage], bytes);
+              mbar_expect_tx_addr(fb, bytes);
             } else {
-              mbar_expect_tx(&S.full[stage], 2 * bytes);
-              bulk_g2s(ringR + stage * sR, rr, bytes, &S.full[stage]);
+              mbar_expect_tx_addr(fb, 2 * bytes);
+              bulk_g2s_addr(ringR + stage * sR, rr + j.r_off, bytes, fb);
             }
-            bulk_g2s(ringC + stage * sC, cc, bytes, &S.full[stage]);
+            bulk_g2s_addr(ringC + stage * sC, cc + j.c_off, bytes, fb);
           }
-          __syncwarp();
           if (++stage == nst) { stage = 0; phase ^= 1; }
-          if (!is_fixed && ++jidx == P.n_cand_jobs) { jidx = 0; ++c; }
+        };
+        for (int j = 0; j < P.n_fixed_jobs; ++j) issue(S.jobs[j], r_cur, c_cur);
+        const uint8_t* r_cand = P.R_cand + rt * P.R_cand_tile_bytes + (size_t)f.c0 * P.R_cand_stride;
+        const uint8_t* c_cand = P.C_cand + ct * P.C_cand_tile_bytes + (size_t)f.c0 * P.C_cand_stride;
+        if (P.n_cand_jobs == 1) {              // the common single-slab step: the job is loop invariant
+          const P4VJob j = S.jobs[P.n_fixed_jobs];
+          const uint8_t* rr = (j.flags & P4V_JOB_RCAND) ? r_cand : r_cur;
+          const uint8_t* cc = (j.flags & P4V_JOB_CCAND) ? c_cand : c_cur;
+          const size_t rstep = (j.flags & P4V_JOB_RCAND) ? P.R_cand_stride : 0, cstep = (j.flags & P4V_JOB_CCAND) ? P.C_cand_stride : 0;
+          for (int c = f.c0; c < f.c1; ++c) { issue(j, rr, cc); rr += rstep; cc += cstep; }
+        } else {
+          for (int c = f.c0; c < f.c1; ++c) {
+            for (int jj = 0; jj < P.n_cand_jobs; ++jj) {
+              const P4VJob j = S.jobs[P.n_fixed_jobs + jj];
+              issue(j, (j.flags & P4V_JOB_RCAND) ? r_cand : r_cur, (j.flags & P4V_JOB_CCAND) ? c_cand : c_cur);
+            }
+            r_cand += P.R_cand_stride; c_cand += P.C_cand_stride;
+          }
         }
       }
     }
@@ -403,45 +454,49 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
     // ======================= MMA issuer (whole warp runs the loop, one elected lane issues) =======================
     {
       uint32_t stage = 0, phase = 0, slot = 0, slot_phase = 0, rbuf = 0, rphase = 0;
-      int tr_n = 0;
-      while (next_frag(P, sched, f)) {
-        uint32_t res_base = 0;
-        const int n_issue = P.n_fixed_jobs + (f.c1 - f.c0) * P.n_cand_jobs;
-        int jidx = 0;
-        for (int it = 0; it < n_issue; ++it) {
-          const bool is_fixed = it < P.n_fixed_jobs;
-          if (resB && it == P.n_fixed_jobs) {       // first candidate job of the fragment: resident row operand landed?
-            mbar_wait(&S.res_full[rbuf], rphase);
-            res_base = resR + rbuf * resB;
-          }
-          const P4VJob j = S.jobs[is_fixed ? it : P.n_fixed_jobs + jidx];
-          const long long tr0 = P.trace ? clock64() : 0;
-          if (j.flags & P4V_JOB_FIRST) mbar_wait(&S.acc_empty[slot], slot_phase ^ 1);
-          mbar_wait(&S.full[stage], phase);
-          tc_fence_after();
-          const long long tr1 = P.trace ? clock64() : 0;
-          const uint32_t ra = (j.flags & P4V_JOB_RRES) ? res_base + j.res_off : ringR + stage * sR;
-          const uint32_t ca = ringC + stage * sC;
+      const uint32_t full0 = smem_u32(&S.full[0]), empty0 = smem_u32(&S.empty[0]);
+      const uint32_t accf0 = smem_u32(&S.acc_full[0]), acce0 = smem_u32(&S.acc_empty[0]);
+      const uint64_t dconst = desc_hi_const();
+      const uint32_t sR16 = sR >> 4, sC16 = sC >> 4, ringR16 = (ringR & 0x3FFFF) >> 4, ringC16 = (ringC & 0x3FFFF) >> 4;
+      // one job: wait (slot if FIRST, stage), K-steps into TMEM slot, hand the stage back, publish the accumulator if LAST
+      auto run = [&](const uint32_t kb, const uint32_t flags, const uint32_t ra16) {
+        if (flags & P4V_JOB_FIRST) mbar_wait_addr(acce0 + slot * 8, slot_phase ^ 1);
+        mbar_wait_addr(full0 + stage * 8, phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t da = dconst | (uint64_t)((flags & P4V_JOB_RRES) ? ra16 : ringR16 + stage * sR16);
+          const uint64_t db = dconst | (uint64_t)(ringC16 + stage * sC16);
           const uint32_t d = tmem + kAccBase + slot * kAccCols;
-          const int ksteps = j.kb >> 5;
-          if (elect_one()) {
-            for (int k = 0; k < ksteps; ++k)
-              umma<kInt8>(d, make_desc(ra + k * 2 * P4V_TILE * 16), make_desc(ca + k * 2 * P4V_TILE * 16),
-                          ((j.flags & P4V_JOB_FIRST) && k == 0) ? 0u : 1u);
-            tc_commit(&S.empty[stage]);
-            if (j.flags & P4V_JOB_LAST) tc_commit(&S.acc_full[slot]);
-          }
-          __syncwarp();
-          if (P.trace && blockIdx.x == 0 && lane == 0 && tr_n < 512) {
-            long long* e = P.trace + (1 * 512 + tr_n) * 4; e[0] = tr0; e[1] = tr1; e[2] = clock64(); e[3] = it; ++tr_n;
-          }
-          if (j.flags & P4V_JOB_LAST) { if (++slot == kSlots) { slot = 0; slot_phase ^= 1; } }
-          if (++stage == nst) { stage = 0; phase ^= 1; }
-          if (!is_fixed && ++jidx == P.n_cand_jobs) jidx = 0;
+          umma<kInt8>(d, da, db, (flags & P4V_JOB_FIRST) ? 0u : 1u);
+          if (kb > 32) umma<kInt8>(d, da + 256, db + 256, 1u);
+          if (kb > 64) umma<kInt8>(d, da + 512, db + 512, 1u);
+          if (kb > 96) umma<kInt8>(d, da + 768, db + 768, 1u);
+          tc_commit_addr(empty0 + stage * 8);
+          if (flags & P4V_JOB_LAST) tc_commit_addr(accf0 + slot * 8);
+        }
+        if (flags & P4V_JOB_LAST) { if (++slot == kSlots) { slot = 0; slot_phase ^= 1; } }
+        if (++stage == nst) { stage = 0; phase ^= 1; }
+      };
+      while (next_frag(P, sched, f)) {
+        for (int j = 0; j < P.n_fixed_jobs; ++j) { const P4VJob jb = S.jobs[j]; run(jb.kb, jb.flags, 0u); }
+        uint32_t res16 = 0;
+        if (resB) {
+          mbar_wait(&S.res_full[rbuf], rphase);
+          res16 = ((resR + rbuf * resB) & 0x3FFFF) >> 4;
+        }
+        if (P.n_cand_jobs == 1) {              // loop-invariant job: keep its fields in registers
+          const P4VJob jb = S.jobs[P.n_fixed_jobs];
+          const uint32_t kb = jb.kb, fl = jb.flags, ra16 = res16 + (jb.res_off >> 4);
+          for (int c = f.c0; c < f.c1; ++c) run(kb, fl, ra16);
+        } else {
+          for (int c = f.c0; c < f.c1; ++c)
+            for (int jj = 0; jj < P.n_cand_jobs; ++jj) {
+              const P4VJob jb = S.jobs[P.n_fixed_jobs + jj];
+              run(jb.kb, jb.flags, res16 + (jb.res_off >> 4));
+            }
         }
         if (resB) {
           if (elect_one()) tc_commit(&S.res_empty[rbuf]);   // resident buffer free once every MMA reading it has retired
-          __syncwarp();
           if (++rbuf == 2) { rbuf = 0; rphase ^= 1; }
         }
       }
@@ -460,7 +515,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
     const float gs = (P.out && !P.out_residual) ? 1.f : *P.gscale;
     AccRing ring{0u, 0u, kSlots};
     float r[64], g[64];
-    uint32_t a0[32], a1[32];
+    uint32_t a0[16], a1[16];
 
     while (next_frag(P, sched, f)) {
       // -- scale tables for this tile's 8 column groups --
@@ -532,27 +587,17 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
       float* part_base = P.partial + ((size_t)f.tile * P.n_cand) * 32 + quarter * 8 + hf * 4;
 
       if constexpr (kSingle) {
-        // -- one accumulator per candidate; two candidates per cross-row reduction --
+        // -- one accumulator per candidate --
         if (f.c1 > f.c0) acc_begin(S, ring, tbase, a0);
-        for (int cb0 = f.c0; cb0 < f.c1; cb0 += 2) {
-          float v[8];
-#pragma unroll
-          for (int ci = 0; ci < 2; ++ci) {
-            float p[4] = {0.f, 0.f, 0.f, 0.f};
-            const int c = cb0 + ci;
-            if (c < f.c1) {
-              const float4 ca = *reinterpret_cast<const float4*>(&S.candA[c][hf * 4]);
-              const float4 cb = *reinterpret_cast<const float4*>(&S.candB[0][hf * 4]);
-              const bool noA = P.cand_noA_mask & 1ull;
-              const float4 sc = noA ? cb : make_float4(ca.x * cb.x, ca.y * cb.y, ca.z * cb.z, ca.w * cb.w);
-              acc_step<kInt8, true, kPacked>(S, ring, tbase, lane, a0, a1, r, g, sc, p, c + 1 < f.c1);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) v[ci * 4 + i] = p[i];
-          }
-          const float tot = reduce8_over_rows(v, lane);
-          const int ci = (lane >> 4) & 1, gi4 = ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-          if (!(lane & 3) && cb0 + ci < f.c1) part_base[(size_t)(cb0 + ci) * 32 + gi4] = tot;
+        const float4 cb = *reinterpret_cast<const float4*>(&S.candB[0][hf * 4]);
+        const bool noA = P.cand_noA_mask & 1ull;
+        for (int c = f.c0; c < f.c1; ++c) {
+          float p[4];
+          const float4 ca = *reinterpret_cast<const float4*>(&S.candA[c][hf * 4]);
+          const float4 sc = noA ? cb : make_float4(ca.x * cb.x, ca.y * cb.y, ca.z * cb.z, ca.w * cb.w);
+          acc_step<kInt8, true, kPacked>(S, ring, tbase, lane, a0, a1, r, g, sc, p, c + 1 < f.c1);
+          const float tot = reduce4_over_rows(p[0], p[1], p[2], p[3], lane);
+          if ((lane & 7) == 0) part_base[(size_t)c * 32 + (lane >> 3)] = tot;
         }
       } else {
         // -- several segments per candidate: park the residual target in TMEM columns [0,128) --
