@@ -30,14 +30,17 @@ enum : uint8_t {
   P4V_JOB_RCAND  = 4,   // row operand comes from the candidate plane
   P4V_JOB_CCAND  = 8,   // column operand comes from the candidate plane
   P4V_JOB_RRES   = 16,  // row operand is candidate independent: loaded once per tile fragment (resident), not per job
+  P4V_JOB_CRES   = 32,  // column operand comes from the tile's resident copy of the current column image
 };
 
 struct __align__(16) P4VJob {
   uint32_t r_off;      // byte offset inside the row-operand tile image
   uint32_t c_off;      // byte offset inside the column-operand tile image
-  uint16_t kb;         // bytes of K per row (multiple of 32, <= P4V_JOB_KB)
+  uint8_t  kb;         // bytes of K per row and per sub-accumulator (multiple of 32; kb * nsub <= P4V_JOB_KB)
+  uint8_t  nsub;       // 0/1: one accumulator (FIRST/LAST chain rules apply); n > 1: the stage holds n consecutive K slabs,
+                       //      each its own accumulator (groups group .. group+n-1), operand offsets advance by kb*128 bytes
   uint8_t  flags;
-  uint8_t  group;      // accumulator group index (row of the scale table)
+  uint8_t  group;      // accumulator group index (row of the scale table) of the first sub-accumulator
   uint32_t res_off;    // byte offset inside the resident row-operand buffer (P4V_JOB_RRES)
 };
 
@@ -71,11 +74,15 @@ struct SweepParams {
   int order;                // 0: tile_m fastest, 1: tile_n fastest
   int is_int8;
   // shared-memory plan, filled by the launcher
-  unsigned int stage_r_bytes, stage_c_bytes, n_stages, resident_bytes;
+  unsigned int stage_r_bytes, stage_c_bytes, n_stages, resident_bytes, resident_bufs, cres_bytes;
   long long* trace;         // debug: clock64 timeline of CTA 0 ([3 roles][512 events][4]) or null
+  int mma_warps;            // 1 or 2 MMA issuer warps (launcher; env P4V_MMA_WARPS)
+  int debug_mode;           // debug (env P4V_SWEEP_DEBUG): 1 = no operand traffic / no MMA (epilogue + handshakes only), 2 = epilogue does no math
 };
 
 static inline __host__ __device__ int p4v_cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline __host__ __device__ unsigned p4v_job_nsub(const P4VJob& j) { return j.nsub ? j.nsub : 1u; }
+static inline __host__ __device__ unsigned p4v_job_bytes(const P4VJob& j) { return (unsigned)j.kb * p4v_job_nsub(j) * P4V_TILE; }   // per operand
 
 // ---- error plumbing (host) --------------------------------------------------
 #ifdef __cplusplus

@@ -29,6 +29,8 @@ static bool g_prof = false;
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_events;
 static std::vector<cudaEvent_t> g_prof_pool;
 static double g_prof_ops = 0.0;
+struct ProfMeta { int n_cand, nfg, ncg, nfj, ncj, i8, out; long long tiles; };
+static std::vector<ProfMeta> g_prof_meta;
 static cudaEvent_t prof_event() {
   if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
   cudaEvent_t e; cudaEventCreate(&e); return e;
@@ -36,25 +38,34 @@ static cudaEvent_t prof_event() {
 extern "C" int p4v_profile_enable(int on) { g_prof = on != 0; return 0; }
 extern "C" int p4v_profile_collect(double* sweep_ms, long long* sweep_launches, double* executed_ops) {
   double ms = 0.0;
+  static const bool log_each = getenv("P4V_PROFILE_LOG") != nullptr;   // debug: one stderr line per sweep launch
+  size_t idx = 0;
   for (auto& pr : g_prof_events) {
     P4V_CUDA_OK(cudaEventSynchronize(pr.second));
     float t = 0.f;
     P4V_CUDA_OK(cudaEventElapsedTime(&t, pr.first, pr.second));
     ms += t;
+    if (log_each && idx < g_prof_meta.size()) {
+      const ProfMeta& m = g_prof_meta[idx];
+      const double accs = (double)m.tiles * (m.nfg + (double)m.ncg * m.n_cand);
+      fprintf(stderr, "[p4v sweep] %8.1f us  cand=%d fixed_groups=%d cand_groups=%d fixed_jobs=%d cand_jobs=%d int8=%d out=%d tiles=%lld  cycles/acc@1.965GHz/148=%.0f\n",
+              t * 1e3, m.n_cand, m.nfg, m.ncg, m.nfj, m.ncj, m.i8, m.out, m.tiles, t * 1e-3 * 1.965e9 * 148.0 / accs);
+    }
+    ++idx;
     g_prof_pool.push_back(pr.first); g_prof_pool.push_back(pr.second);
   }
   if (sweep_ms) *sweep_ms = ms;
   if (sweep_launches) *sweep_launches = (long long)g_prof_events.size();
   if (executed_ops) *executed_ops = g_prof_ops;
-  g_prof_events.clear(); g_prof_ops = 0.0;
+  g_prof_events.clear(); g_prof_meta.clear(); g_prof_ops = 0.0;
   return 0;
 }
 // tensor-core work of one sweep launch: every job multiplies a 128x128 tile over kb bytes of K
 static double sweep_ops(const SweepParams& sp, const P4VJob* host_jobs) {
   double kf = 0.0, kc = 0.0;
   const double ew = sp.is_int8 ? 1.0 : 2.0;
-  for (int j = 0; j < sp.n_fixed_jobs; ++j) kf += host_jobs[j].kb / ew;
-  for (int j = 0; j < sp.n_cand_jobs; ++j) kc += host_jobs[sp.n_fixed_jobs + j].kb / ew;
+  for (int j = 0; j < sp.n_fixed_jobs; ++j) kf += host_jobs[j].kb * p4v_job_nsub(host_jobs[j]) / ew;
+  for (int j = 0; j < sp.n_cand_jobs; ++j) kc += host_jobs[sp.n_fixed_jobs + j].kb * p4v_job_nsub(host_jobs[sp.n_fixed_jobs + j]) / ew;
   const double tiles = (double)sp.P * sp.tiles_m * sp.tiles_n;
   return 2.0 * P4V_TILE * P4V_TILE * tiles * (kf + kc * sp.n_cand);
 }
@@ -66,7 +77,8 @@ int p4v_run_sweep(const SweepParams& sp_in, const P4VJob* host_jobs, int kernel,
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (g_prof) { e0 = prof_event(); e1 = prof_event(); cudaEventRecord(e0, st); }
   int rc = kernel == P4V_KERNEL_SIMT ? p4v_launch_sweep_simt(sp, st) : p4v_launch_sweep_tc(sp, host_jobs, p4v_num_sms(), st);
-  if (g_prof) { cudaEventRecord(e1, st); g_prof_events.emplace_back(e0, e1); g_prof_ops += sweep_ops(sp, host_jobs); }
+  if (g_prof) { cudaEventRecord(e1, st); g_prof_events.emplace_back(e0, e1); g_prof_ops += sweep_ops(sp, host_jobs);
+    g_prof_meta.push_back(ProfMeta{sp.n_cand, sp.n_fixed_groups, sp.n_cand_groups, sp.n_fixed_jobs, sp.n_cand_jobs, sp.is_int8, sp.out != nullptr, (long long)sp.P * sp.tiles_m * sp.tiles_n}); }
   return rc;
 }
 
@@ -117,7 +129,7 @@ void add_group(LinPlan& p, int r_off_bytes, int c_off_bytes, int kb, uint8_t src
     const int len = std::min(P4V_JOB_KB, kb - b);
     j.r_off = (uint32_t)(r_off_bytes + b) * P4V_TILE;
     j.c_off = (uint32_t)(c_off_bytes + b) * P4V_TILE;
-    j.kb = (uint16_t)len;
+    j.kb = (uint8_t)len;
     j.flags = src_flags | (b == 0 ? P4V_JOB_FIRST : 0) | (b + len >= kb ? P4V_JOB_LAST : 0);
     j.group = (uint8_t)group_idx;
     p.jobs.push_back(j);
@@ -136,6 +148,31 @@ void mark_resident(LinPlan& p, const Step& st) {
     if (jb.flags & P4V_JOB_RCAND) return;
     jb.flags |= P4V_JOB_RRES; jb.res_off = off; off += (uint32_t)jb.kb * P4V_TILE;
   }
+}
+
+// Merge runs of single-job accumulator groups whose K slabs are adjacent in BOTH operand images into one
+// stage load with several sub-accumulators (one bulk copy / one stage handshake for up to 128 bytes of K).
+void batch_jobs(LinPlan& p, int first, int& count) {
+  std::vector<P4VJob> out;
+  for (int j = 0; j < count; ++j) {
+    const P4VJob jb = p.jobs[first + j];
+    const bool single = (jb.flags & P4V_JOB_FIRST) && (jb.flags & P4V_JOB_LAST) && !(jb.flags & (P4V_JOB_RRES | P4V_JOB_CCAND));
+    if (single && !out.empty()) {
+      P4VJob& prev = out.back();
+      const unsigned n = p4v_job_nsub(prev);
+      const bool prev_single = (prev.flags & P4V_JOB_FIRST) && (prev.flags & P4V_JOB_LAST);
+      if (prev_single && prev.flags == jb.flags && prev.kb == jb.kb && (n + 1) * jb.kb <= P4V_JOB_KB &&
+          prev.r_off + n * jb.kb * P4V_TILE == jb.r_off && prev.c_off + n * jb.kb * P4V_TILE == jb.c_off &&
+          prev.group + n == jb.group) {
+        prev.nsub = (uint8_t)(n + 1);
+        continue;
+      }
+    }
+    out.push_back(jb);
+  }
+  std::copy(out.begin(), out.end(), p.jobs.begin() + first);
+  p.jobs.erase(p.jobs.begin() + first + out.size(), p.jobs.begin() + first + count);
+  count = (int)out.size();
 }
 
 int build_plan(const p4v_linear_desc* d, LinPlan& p, bool with_search) {
@@ -167,7 +204,7 @@ int build_plan(const p4v_linear_desc* d, LinPlan& p, bool with_search) {
   for (size_t i = 0; i + 1 < cuts.size(); ++i) min_len = std::min(min_len, cuts[i + 1] - cuts[i]);
   if (d->operand == P4V_OPERAND_INT8) p.i8 = true;
   else if (d->operand == P4V_OPERAND_BF16) p.i8 = false;
-  else p.i8 = min_len >= 64;     // short slabs are epilogue bound: integer-valued bf16 saves the int->float converts
+  else p.i8 = min_len >= 32;     // one kind::i8 K-step (32 elements) per slab or more: half the operand bytes of bf16
   p.ew = p.i8 ? 1 : 2;
   p.segs.clear();
   int off = 0;
@@ -231,6 +268,7 @@ int build_plan(const p4v_linear_desc* d, LinPlan& p, bool with_search) {
         st.commit_chunks += s.kb / 16; ++st.ncommit;
       }
       mark_resident(p, st);
+      batch_jobs(p, st.job_off, st.nfj);
       p.wsteps.push_back(st);
     }
     for (int a = 0; a < d->n_a; ++a) {
@@ -244,6 +282,12 @@ int build_plan(const p4v_linear_desc* d, LinPlan& p, bool with_search) {
         p.commits.push_back(CommitSeg{s.xcoff * P4V_TILE, s.xoff_p * P4V_TILE, s.kb});
         st.commit_chunks += s.kb / 16; ++st.ncommit;
       }
+      {   // candidates change the row operand only: keep the tile's weight image resident when it fits
+        int ncj = st.ncj; batch_jobs(p, st.job_off + st.nfj, ncj); st.ncj = ncj;
+        batch_jobs(p, st.job_off, st.nfj);
+        if ((size_t)p.KB_W * P4V_TILE <= 100 * 1024 && getenv("P4V_NO_CRES") == nullptr)
+          for (int j = 0; j < st.nfj + st.ncj; ++j) p.jobs[st.job_off + j].flags |= P4V_JOB_CRES;
+      }
       p.xsteps.push_back(st);
     }
   }
@@ -252,6 +296,7 @@ int build_plan(const p4v_linear_desc* d, LinPlan& p, bool with_search) {
     st.meta_fix = (int)p.metas.size();
     for (auto& s : p.segs) { fixed_group(st, s, false); if (p.twin) fixed_group(st, s, true); }
     st.meta_cand = (int)p.metas.size();
+    batch_jobs(p, st.job_off, st.nfj);
     p.fwd = st;
   }
   auto check = [&](const Step& st) {
@@ -308,7 +353,7 @@ int build_plan(const p4v_linear_desc* d, LinPlan& p, bool with_search) {
           P4VJob jb{};
           const unsigned b = (unsigned)j * P4V_JOB_KB;
           jb.r_off = (combos[gi][0] * term + b) * P4V_TILE; jb.c_off = (combos[gi][1] * term + b) * P4V_TILE;
-          jb.kb = (uint16_t)std::min<unsigned>(P4V_JOB_KB, term - b);
+          jb.kb = (uint8_t)std::min<unsigned>(P4V_JOB_KB, term - b);
           jb.flags = (j == 0 ? P4V_JOB_FIRST : 0) | (j == nj - 1 ? P4V_JOB_LAST : 0);
           jb.group = (uint8_t)gi;
           p.gjobs.push_back(jb);

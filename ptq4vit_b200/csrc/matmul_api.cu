@@ -39,7 +39,7 @@ void push_jobs(MMPlan& p, int r_off, int c_off, int kb, uint8_t src, int group, 
   for (int b = 0; b < kb; b += P4V_JOB_KB) {
     P4VJob j{};
     const int len = std::min(P4V_JOB_KB, kb - b);
-    j.r_off = (uint32_t)(r_off + b) * P4V_TILE; j.c_off = (uint32_t)(c_off + b) * P4V_TILE; j.kb = (uint16_t)len;
+    j.r_off = (uint32_t)(r_off + b) * P4V_TILE; j.c_off = (uint32_t)(c_off + b) * P4V_TILE; j.kb = (uint8_t)len;
     j.flags = src | ((first && b == 0) ? P4V_JOB_FIRST : 0) | ((last && b + len >= kb) ? P4V_JOB_LAST : 0);
     j.group = (uint8_t)group;
     p.jobs.push_back(j); ++n;

@@ -66,21 +66,28 @@ __global__ void __launch_bounds__(256) sweep_simt_kernel(const __grid_constant__
       float acc = 0.f;
       for (int j = 0; j < P.n_fixed_jobs; ++j) {
         const P4VJob jb = P.jobs[j];
-        if (jb.flags & P4V_JOB_FIRST) acc = 0.f;
-        acc += dot_job<kInt8>(Rcur + jb.r_off, Ccur + jb.c_off, row, col, jb.kb);
-        if (jb.flags & P4V_JOB_LAST) r = fmaf(-P.fix_scale[(size_t)jb.group * P.nsg + sg], acc, r);
+        for (unsigned sub = 0; sub < p4v_job_nsub(jb); ++sub) {
+          const size_t so = (size_t)sub * jb.kb * P4V_TILE;
+          if (jb.flags & P4V_JOB_FIRST) acc = 0.f;
+          acc += dot_job<kInt8>(Rcur + jb.r_off + so, Ccur + jb.c_off + so, row, col, jb.kb);
+          if (jb.flags & P4V_JOB_LAST) r = fmaf(-P.fix_scale[(size_t)(jb.group + sub) * P.nsg + sg], acc, r);
+        }
       }
       if (P.out) { P.out[off] = P.out_residual ? r : -r; continue; }
       for (int j = 0; j < P.n_cand_jobs; ++j) {
         const P4VJob jb = P.jobs[P.n_fixed_jobs + j];
-        if (jb.flags & P4V_JOB_FIRST) acc = 0.f;
-        const uint8_t* rr = ((jb.flags & P4V_JOB_RCAND) ? Rcand : Rcur) + jb.r_off;
-        const uint8_t* cc = ((jb.flags & P4V_JOB_CCAND) ? Ccand : Ccur) + jb.c_off;
-        acc += dot_job<kInt8>(rr, cc, row, col, jb.kb);
-        if (jb.flags & P4V_JOB_LAST) {
-          const float cb = P.candB[(size_t)jb.group * P.nsg + sg];
-          const float s = ((P.cand_noA_mask >> jb.group) & 1ull) ? cb : P.candA[(size_t)c * P.nsg + sg] * cb;
-          r = fmaf(-s, acc, r);
+        for (unsigned sub = 0; sub < p4v_job_nsub(jb); ++sub) {
+          const size_t so = (size_t)sub * jb.kb * P4V_TILE;
+          const unsigned grp = jb.group + sub;
+          if (jb.flags & P4V_JOB_FIRST) acc = 0.f;
+          const uint8_t* rr = ((jb.flags & P4V_JOB_RCAND) ? Rcand : Rcur) + jb.r_off + so;
+          const uint8_t* cc = ((jb.flags & P4V_JOB_CCAND) ? Ccand : Ccur) + jb.c_off + so;
+          acc += dot_job<kInt8>(rr, cc, row, col, jb.kb);
+          if (jb.flags & P4V_JOB_LAST) {
+            const float cb = P.candB[(size_t)grp * P.nsg + sg];
+            const float s = ((P.cand_noA_mask >> grp) & 1ull) ? cb : P.candA[(size_t)c * P.nsg + sg] * cb;
+            r = fmaf(-s, acc, r);
+          }
         }
       }
       const float w = g * r;

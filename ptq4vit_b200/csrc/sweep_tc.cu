@@ -24,13 +24,26 @@
 
 namespace {
 
+#ifdef P4V_TRACE   // debug build only: clock64 timeline of CTA 0 (tools/trace_sweep.py)
+#define TRACE(role, ev, col) do { if (P.trace && blockIdx.x == 0 && (ev) < 512 && (threadIdx.x & 31) == 0) P.trace[((role) * 512 + (ev)) * 4 + (col)] = clock64(); } while (0)
+#else
+#define TRACE(role, ev, col) do { } while (0)
+#endif
+
 constexpr int kMaxStages = 16;
 constexpr int kAccCols = 128;
 constexpr int kTmemCols = 512;
 constexpr int kEpiThreads = 256;
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 128 + kEpiThreads;   // warpgroup 0: producer, MMA, 2 idle warps; warpgroups 1-2: epilogue
-constexpr int kSmemBudget = 200 * 1024;       // ring + resident operand
+constexpr int kSmemBudget = 200 * 1024;       // ring + resident operand (+ score reduction buffers of the single-segment steps)
+// Score reduction of the single-segment steps: every epilogue thread drops its 4 per-group sums of one candidate into
+// shared memory (one conflict-free 16-byte store, no shuffle chain); every kRedBatch candidates the 256 threads sum
+// the 128 rows of each (candidate, group) in 4 row quarters.  Layout [buffer][candidate][column half][row][4].
+constexpr int kRedBatch = 8;
+constexpr int kRedHalf = P4V_TILE * 4 + 4;    // floats; +4 shifts the second column half by four banks
+constexpr int kRedCand = 2 * kRedHalf;
+constexpr int kRedBytes = 2 * kRedBatch * kRedCand * 4;
 
 struct SmemCtl {
   alignas(16) P4VJob jobs[P4V_MAX_JOBS];
@@ -43,6 +56,7 @@ struct SmemCtl {
   unsigned long long acc_empty[4];
   unsigned long long res_full[2];
   unsigned long long res_empty[2];
+  unsigned long long cres_full, cres_empty;
   uint32_t tmem_base;
 };
 
@@ -332,8 +346,23 @@ __device__ __forceinline__ void acc_begin(SmemCtl& S, AccRing& ring, uint32_t tb
 template <bool kInt8, bool kScore, bool kPacked>
 __device__ __forceinline__ void acc_step(SmemCtl& S, AccRing& ring, uint32_t tbase, int lane, uint32_t (&a0)[16],
                                          uint32_t (&a1)[16], float (&r)[64], const float (&g)[64], const float4 sc,
-                                         float (&p)[4], const bool has_next) {
+                                         float (&p)[4], const bool has_next, const bool skip_math = false) {
   const uint32_t t0 = tbase + ring.slot * kAccCols;
+  uint32_t nslot = ring.slot + 1, nphase = ring.phase;
+  if (nslot == ring.nslots) { nslot = 0; nphase ^= 1; }
+  if (skip_math) {                 // debug mode 2: handshakes only
+    p[0] = p[1] = p[2] = p[3] = 0.f;
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&S.acc_empty[ring.slot]);
+    ring.slot = nslot; ring.phase = nphase;
+    if (has_next) { mbar_wait(&S.acc_full[ring.slot], ring.phase); tc_fence_after(); }
+    return;
+  }
+  // non-blocking probe of the NEXT accumulator's barrier: its latency hides behind this accumulator's math
+  const uint32_t next_bar = smem_u32(&S.acc_full[nslot]);
+  bool next_ready = true;
+  if (has_next) next_ready = mbar_try(next_bar, nphase);
   tmem_ld16(t0 + 16, a1);
   consume16<kInt8, kScore, kPacked, 0>(a0, r, g, sc.x, p[0]);
   tmem_wait_ld();
@@ -346,13 +375,101 @@ __device__ __forceinline__ void acc_step(SmemCtl& S, AccRing& ring, uint32_t tba
   tc_fence_before();
   __syncwarp();
   if (lane == 0) mbar_arrive(&S.acc_empty[ring.slot]);      // one arrival per epilogue warp
-  if (++ring.slot == ring.nslots) { ring.slot = 0; ring.phase ^= 1; }
+  ring.slot = nslot; ring.phase = nphase;
   if (has_next) {
-    mbar_wait(&S.acc_full[ring.slot], ring.phase);
+    if (!next_ready) mbar_wait(&S.acc_full[nslot], nphase);
     tc_fence_after();
-    tmem_ld16(tbase + ring.slot * kAccCols, a0);
+    tmem_ld16(tbase + nslot * kAccCols, a0);
   }
   consume16<kInt8, kScore, kPacked, 48>(a1, r, g, sc.w, p[3]);
+  if (has_next) tmem_wait_ld();
+}
+
+
+// ---- multi-segment steps: 32-column halves, gradient tile parked in shared memory ----------------------------
+// Steps with many accumulators per candidate (activation steps) spend one FMA per element on all but the last
+// accumulator, so a 16-column quarter does not cover the latency of the next TMEM load.  Here the gradient tile is
+// NOT kept in registers (it is needed once per candidate); the registers hold two 32-column halves instead.
+__device__ __forceinline__ void tmem_ld32u(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+// gp: this thread's row of the parked gradient tile, [column quad][128 rows] float4 (quad stride = 128 float4)
+template <bool kInt8, bool kScore, bool kPacked, int OFF>
+__device__ __forceinline__ void consume32(const uint32_t (&a)[32], float (&r)[64], const float4* gp, const float s0,
+                                          const float s1, float& p0, float& p1) {
+  if constexpr (!kScore) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      const float s = j < 16 ? s0 : s1;
+      if constexpr (kPacked) {
+        const f32x2 d = fma2(pack2(-s, -s), pack2(acc_to_float<kInt8>(a[j]), acc_to_float<kInt8>(a[j + 1])), pack2(r[OFF + j], r[OFF + j + 1]));
+        unpack2(d, r[OFF + j], r[OFF + j + 1]);
+      } else {
+        r[OFF + j] = fmaf(-s, acc_to_float<kInt8>(a[j]), r[OFF + j]);
+        r[OFF + j + 1] = fmaf(-s, acc_to_float<kInt8>(a[j + 1]), r[OFF + j + 1]);
+      }
+    }
+  } else {
+    float q[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float4 gv = gp[(OFF / 4 + k) * P4V_TILE];
+      const float s = k < 4 ? s0 : s1;
+      const int j = 4 * k;
+      const float d0 = fmaf(-s, acc_to_float<kInt8>(a[j]), r[OFF + j]), d1 = fmaf(-s, acc_to_float<kInt8>(a[j + 1]), r[OFF + j + 1]);
+      const float d2 = fmaf(-s, acc_to_float<kInt8>(a[j + 2]), r[OFF + j + 2]), d3 = fmaf(-s, acc_to_float<kInt8>(a[j + 3]), r[OFF + j + 3]);
+      const float w0 = gv.x * d0, w1 = gv.y * d1, w2 = gv.z * d2, w3 = gv.w * d3;
+      float& qa = q[(k < 4 ? 0 : 2)]; float& qb = q[(k < 4 ? 1 : 3)];
+      qa = fmaf(w0, w0, qa); qb = fmaf(w1, w1, qb); qa = fmaf(w2, w2, qa); qb = fmaf(w3, w3, qb);
+    }
+    p0 = q[0] + q[1]; p1 = q[2] + q[3];
+  }
+}
+__device__ __forceinline__ void accm_begin(SmemCtl& S, AccRing& ring, uint32_t tbase, uint32_t (&a0)[32]) {
+  mbar_wait(&S.acc_full[ring.slot], ring.phase);
+  tc_fence_after();
+  tmem_ld32u(tbase + ring.slot * kAccCols, a0);
+  tmem_wait_ld();
+}
+template <bool kInt8, bool kScore, bool kPacked>
+__device__ __forceinline__ void accm_step(SmemCtl& S, AccRing& ring, uint32_t tbase, int lane, uint32_t (&a0)[32],
+                                          uint32_t (&a1)[32], float (&r)[64], const float4* gp, const float4 sc,
+                                          float (&p)[4], const bool has_next, const bool skip_math) {
+  const uint32_t t0 = tbase + ring.slot * kAccCols;
+  uint32_t nslot = ring.slot + 1, nphase = ring.phase;
+  if (nslot == ring.nslots) { nslot = 0; nphase ^= 1; }
+  if (skip_math) {                 // debug mode 2: handshakes only
+    p[0] = p[1] = p[2] = p[3] = 0.f;
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&S.acc_empty[ring.slot]);
+    ring.slot = nslot; ring.phase = nphase;
+    if (has_next) { mbar_wait(&S.acc_full[ring.slot], ring.phase); tc_fence_after(); }
+    return;
+  }
+  bool next_ready = true;
+  if (has_next) next_ready = mbar_try(smem_u32(&S.acc_full[nslot]), nphase);
+  tmem_ld32u(t0 + 32, a1);
+  consume32<kInt8, kScore, kPacked, 0>(a0, r, gp, sc.x, sc.y, p[0], p[1]);
+  tmem_wait_ld();
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(&S.acc_empty[ring.slot]);      // one arrival per epilogue warp
+  ring.slot = nslot; ring.phase = nphase;
+  if (has_next) {
+    if (!next_ready) mbar_wait(&S.acc_full[nslot], nphase);
+    tc_fence_after();
+    tmem_ld32u(tbase + nslot * kAccCols, a0);
+  }
+  consume32<kInt8, kScore, kPacked, 32>(a1, r, gp, sc.z, sc.w, p[2], p[3]);
   if (has_next) tmem_wait_ld();
 }
 
@@ -361,9 +478,11 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   // carve: [ring R stages][ring C stages][resident R x2][control]
-  const uint32_t sR = P.stage_r_bytes, sC = P.stage_c_bytes, nst = P.n_stages, resB = P.resident_bytes;
-  const uint32_t ringR = smem_u32(smem), ringC = ringR + nst * sR, resR = ringC + nst * sC;
-  SmemCtl& S = *reinterpret_cast<SmemCtl*>(smem + (size_t)nst * (sR + sC) + 2 * (size_t)resB);
+  const uint32_t sR = P.stage_r_bytes, sC = P.stage_c_bytes, nst = P.n_stages, resB = P.resident_bytes, cresB = P.cres_bytes;
+  const uint32_t ringR = smem_u32(smem), ringC = ringR + nst * sR, resR = ringC + nst * sC, resC = resR + P.resident_bufs * resB;
+  const size_t ctl_off = (size_t)nst * (sR + sC) + (size_t)P.resident_bufs * resB + cresB;
+  SmemCtl& S = *reinterpret_cast<SmemCtl*>(smem + ctl_off);
+  [[maybe_unused]] float* const red = reinterpret_cast<float*>(smem + ctl_off + ((sizeof(SmemCtl) + 127) & ~size_t(127)));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr uint32_t kSlots = kSingle ? 4 : 3;            // single-segment steps do not park the target in TMEM
   constexpr uint32_t kAccBase = kSingle ? 0 : kAccCols;
@@ -374,7 +493,8 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
   if (threadIdx.x == 0) {
     for (uint32_t i = 0; i < nst; ++i) { mbar_init(&S.full[i], 1); mbar_init(&S.empty[i], 1); }
     for (int i = 0; i < 4; ++i) { mbar_init(&S.acc_full[i], 1); mbar_init(&S.acc_empty[i], kEpiWarps); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&S.res_full[i], 1); mbar_init(&S.res_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&S.res_full[i], 1); mbar_init(&S.res_empty[i], P.mma_warps); }
+    mbar_init(&S.cres_full, 1); mbar_init(&S.cres_empty, P.mma_warps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -396,38 +516,48 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
     // Single-warp loop: every instruction is on the critical path of a ~100-instruction-per-job budget, so addresses
     // are advanced incrementally and barrier / stage addresses are plain 32-bit shared-memory offsets.
     {
-      uint32_t stage = 0, phase = 0, rbuf = 0, rphase = 0;
+      uint32_t stage = 0, phase = 0, rbuf = 0, rphase = 0, cphase = 0;
+      [[maybe_unused]] int tev = 0;
       const uint32_t full0 = smem_u32(&S.full[0]), empty0 = smem_u32(&S.empty[0]);
-      while (next_frag(P, sched, f)) {
+      while (!(P.debug_mode & 1) && next_frag(P, sched, f)) {
         const size_t rt = (size_t)(f.p * P.tiles_m + f.tm), ct = (size_t)(f.p * P.tiles_n + f.tn);
         const uint8_t* r_cur = P.R_cur + rt * P.R_tile_bytes;
         const uint8_t* c_cur = P.C_cur + ct * P.C_tile_bytes;
+        if (cresB) {     // the tile's whole current column image: once per fragment (single buffer: wait for the previous tile's MMAs)
+          mbar_wait(&S.cres_empty, cphase ^ 1);
+          if (elect_one()) {
+            mbar_expect_tx(&S.cres_full, cresB);
+            for (uint32_t o = 0; o < cresB; o += 32768u)
+              bulk_g2s(resC + o, c_cur + o, (cresB - o < 32768u) ? cresB - o : 32768u, &S.cres_full);
+          }
+          cphase ^= 1;
+        }
         if (resB) {      // row operand of the candidate jobs: once per fragment, reused by every candidate
           mbar_wait(&S.res_empty[rbuf], rphase ^ 1);
           uint32_t total = 0;
-          for (int j = 0; j < P.n_cand_jobs; ++j) total += (uint32_t)S.jobs[P.n_fixed_jobs + j].kb * P4V_TILE;
+          for (int j = 0; j < P.n_cand_jobs; ++j) total += p4v_job_bytes(S.jobs[P.n_fixed_jobs + j]);
           if (elect_one()) {
             mbar_expect_tx(&S.res_full[rbuf], total);
             for (int j = 0; j < P.n_cand_jobs; ++j) {
               const P4VJob jb = S.jobs[P.n_fixed_jobs + j];
-              bulk_g2s(resR + rbuf * resB + jb.res_off, r_cur + jb.r_off, (uint32_t)jb.kb * P4V_TILE, &S.res_full[rbuf]);
+              bulk_g2s(resR + rbuf * resB + jb.res_off, r_cur + jb.r_off, p4v_job_bytes(jb), &S.res_full[rbuf]);
             }
           }
-          if (++rbuf == 2) { rbuf = 0; rphase ^= 1; }
+          if (++rbuf == P.resident_bufs) { rbuf = 0; rphase ^= 1; }
         }
         auto issue = [&](const P4VJob j, const uint8_t* rr, const uint8_t* cc) {
+          TRACE(0, tev, 0);
           mbar_wait_addr(empty0 + stage * 8, phase ^ 1);
-          const uint32_t bytes = (uint32_t)j.kb * P4V_TILE;
+          TRACE(0, tev, 1);
+          const uint32_t bytes = p4v_job_bytes(j);
           if (elect_one()) {
             const uint32_t fb = full0 + stage * 8;
-            if (j.flags & P4V_JOB_RRES) {
-              mbar_expect_tx_addr(fb, bytes);
-            } else {
-              mbar_expect_tx_addr(fb, 2 * bytes);
-              bulk_g2s_addr(ringR + stage * sR, rr + j.r_off, bytes, fb);
-            }
-            bulk_g2s_addr(ringC + stage * sC, cc + j.c_off, bytes, fb);
+            const uint32_t nload = ((j.flags & P4V_JOB_RRES) ? 0u : 1u) + ((j.flags & P4V_JOB_CRES) ? 0u : 1u);
+            mbar_expect_tx_addr(fb, nload * bytes);
+            if (!(j.flags & P4V_JOB_RRES)) bulk_g2s_addr(ringR + stage * sR, rr + j.r_off, bytes, fb);
+            if (!(j.flags & P4V_JOB_CRES)) bulk_g2s_addr(ringC + stage * sC, cc + j.c_off, bytes, fb);
           }
+          TRACE(0, tev, 2); ++tev;
           if (++stage == nst) { stage = 0; phase ^= 1; }
         };
         for (int j = 0; j < P.n_fixed_jobs; ++j) issue(S.jobs[j], r_cur, c_cur);
@@ -450,8 +580,11 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
         }
       }
     }
-  } else if (warp == 1) {
-    // ======================= MMA issuer (whole warp runs the loop, one elected lane issues) =======================
+  } else if (warp == 1 || (warp == 2 && P.mma_warps == 2)) {
+    // ======================= MMA issuer(s) (whole warp runs the loop, one elected lane issues) =======================
+    // With two issuer warps the jobs (= stages; multi-job accumulation chains stay together) alternate between them:
+    // the owner waits for the stage, issues, and hands the stage and the accumulators on; the other warp only
+    // advances its ring counters.  Each warp's loop is latency bound, two of them double the issue rate.
     {
       uint32_t stage = 0, phase = 0, slot = 0, slot_phase = 0, rbuf = 0, rphase = 0;
       const uint32_t full0 = smem_u32(&S.full[0]), empty0 = smem_u32(&S.empty[0]);
@@ -459,46 +592,73 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
       const uint64_t dconst = desc_hi_const();
       const uint32_t sR16 = sR >> 4, sC16 = sC >> 4, ringR16 = (ringR & 0x3FFFF) >> 4, ringC16 = (ringC & 0x3FFFF) >> 4;
       // one job: wait (slot if FIRST, stage), K-steps into TMEM slot, hand the stage back, publish the accumulator if LAST
-      auto run = [&](const uint32_t kb, const uint32_t flags, const uint32_t ra16) {
-        if (flags & P4V_JOB_FIRST) mbar_wait_addr(acce0 + slot * 8, slot_phase ^ 1);
-        mbar_wait_addr(full0 + stage * 8, phase);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint64_t da = dconst | (uint64_t)((flags & P4V_JOB_RRES) ? ra16 : ringR16 + stage * sR16);
-          const uint64_t db = dconst | (uint64_t)(ringC16 + stage * sC16);
-          const uint32_t d = tmem + kAccBase + slot * kAccCols;
-          umma<kInt8>(d, da, db, (flags & P4V_JOB_FIRST) ? 0u : 1u);
-          if (kb > 32) umma<kInt8>(d, da + 256, db + 256, 1u);
-          if (kb > 64) umma<kInt8>(d, da + 512, db + 512, 1u);
-          if (kb > 96) umma<kInt8>(d, da + 768, db + 768, 1u);
-          tc_commit_addr(empty0 + stage * 8);
-          if (flags & P4V_JOB_LAST) tc_commit_addr(accf0 + slot * 8);
+      [[maybe_unused]] int tev = 0;
+      uint32_t cphase = 0;
+      const uint32_t resC16 = (resC & 0x3FFFF) >> 4;
+      // one job = one stage: wait for its bytes, then per sub-accumulator (slot if FIRST, K-steps, publish if LAST);
+      // the stage goes back to the producer with the last sub-accumulator
+      const uint32_t me = warp - 1, two = P.mma_warps == 2;
+      uint32_t chain = 0;
+      auto run = [&](const P4VJob jb, const uint32_t ra16) {
+        const uint32_t flags = jb.flags, kb = jb.kb, nsub = p4v_job_nsub(jb);
+        const bool mine = !two || (chain & 1u) == me;
+        if (flags & P4V_JOB_LAST) ++chain;
+        if (!mine) {                                    // the other issuer's job: keep the ring counters in step
+          if (flags & P4V_JOB_LAST) for (uint32_t sub = 0; sub < nsub; ++sub) { if (++slot == kSlots) { slot = 0; slot_phase ^= 1; } }
+          if (++stage == nst) { stage = 0; phase ^= 1; }
+          return;
         }
-        if (flags & P4V_JOB_LAST) { if (++slot == kSlots) { slot = 0; slot_phase ^= 1; } }
+        TRACE(1, tev, 0);
+        if (!(P.debug_mode & 1)) mbar_wait_addr(full0 + stage * 8, phase);
+        TRACE(1, tev, 1);
+        tc_fence_after();
+        uint32_t a16 = (flags & P4V_JOB_RRES) ? ra16 : ringR16 + stage * sR16;
+        uint32_t b16 = (flags & P4V_JOB_CRES) ? resC16 + (jb.c_off >> 4) : ringC16 + stage * sC16;
+        for (uint32_t sub = 0; sub < nsub; ++sub) {
+          if (flags & P4V_JOB_FIRST) mbar_wait_addr(acce0 + slot * 8, slot_phase ^ 1);
+          TRACE(1, tev, 2);
+          if (P.debug_mode & 1) {
+            if ((flags & P4V_JOB_LAST) && elect_one()) tc_commit_addr(accf0 + slot * 8);
+          } else if (elect_one()) {
+            const uint64_t da = dconst | (uint64_t)a16, db = dconst | (uint64_t)b16;
+            const uint32_t d = tmem + kAccBase + slot * kAccCols;
+            umma<kInt8>(d, da, db, (flags & P4V_JOB_FIRST) ? 0u : 1u);
+            if (kb > 32) umma<kInt8>(d, da + 256, db + 256, 1u);
+            if (kb > 64) umma<kInt8>(d, da + 512, db + 512, 1u);
+            if (kb > 96) umma<kInt8>(d, da + 768, db + 768, 1u);
+            if (sub + 1 == nsub) tc_commit_addr(empty0 + stage * 8);
+            if (flags & P4V_JOB_LAST) tc_commit_addr(accf0 + slot * 8);
+          }
+          a16 += kb * 8; b16 += kb * 8;        // kb * 128 bytes, in 16-byte units
+          if (flags & P4V_JOB_LAST) { if (++slot == kSlots) { slot = 0; slot_phase ^= 1; } }
+        }
+        TRACE(1, tev, 3); ++tev;
         if (++stage == nst) { stage = 0; phase ^= 1; }
       };
       while (next_frag(P, sched, f)) {
-        for (int j = 0; j < P.n_fixed_jobs; ++j) { const P4VJob jb = S.jobs[j]; run(jb.kb, jb.flags, 0u); }
+        if (cresB) { if (!(P.debug_mode & 1)) mbar_wait(&S.cres_full, cphase); cphase ^= 1; }
+        for (int j = 0; j < P.n_fixed_jobs; ++j) run(S.jobs[j], 0u);
         uint32_t res16 = 0;
         if (resB) {
-          mbar_wait(&S.res_full[rbuf], rphase);
+          if (!(P.debug_mode & 1)) mbar_wait(&S.res_full[rbuf], rphase);
           res16 = ((resR + rbuf * resB) & 0x3FFFF) >> 4;
         }
         if (P.n_cand_jobs == 1) {              // loop-invariant job: keep its fields in registers
           const P4VJob jb = S.jobs[P.n_fixed_jobs];
-          const uint32_t kb = jb.kb, fl = jb.flags, ra16 = res16 + (jb.res_off >> 4);
-          for (int c = f.c0; c < f.c1; ++c) run(kb, fl, ra16);
+          const uint32_t ra16 = res16 + (jb.res_off >> 4);
+          for (int c = f.c0; c < f.c1; ++c) run(jb, ra16);
         } else {
           for (int c = f.c0; c < f.c1; ++c)
             for (int jj = 0; jj < P.n_cand_jobs; ++jj) {
               const P4VJob jb = S.jobs[P.n_fixed_jobs + jj];
-              run(jb.kb, jb.flags, res16 + (jb.res_off >> 4));
+              run(jb, res16 + (jb.res_off >> 4));
             }
         }
         if (resB) {
-          if (elect_one()) tc_commit(&S.res_empty[rbuf]);   // resident buffer free once every MMA reading it has retired
-          if (++rbuf == 2) { rbuf = 0; rphase ^= 1; }
+          if (!(P.debug_mode & 1) && elect_one()) tc_commit(&S.res_empty[rbuf]);   // resident buffer free once every MMA reading it has retired
+          if (++rbuf == P.resident_bufs) { rbuf = 0; rphase ^= 1; }
         }
+        if (cresB && !(P.debug_mode & 1) && elect_one()) tc_commit(&S.cres_empty);
       }
     }
   }
@@ -514,6 +674,105 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
     const uint32_t tstore = tmem + lane_addr + hf * 64;                 // parked residual target (!kSingle)
     const float gs = (P.out && !P.out_residual) ? 1.f : *P.gscale;
     AccRing ring{0u, 0u, kSlots};
+    const bool dbg2 = P.debug_mode & 2;
+    [[maybe_unused]] int tev = 0;
+    if constexpr (!kSingle) {
+    // ---------------- several accumulators per candidate (or output mode) ----------------
+    float r[64];
+    uint32_t a0[32], a1[32];
+    float4* const gp = reinterpret_cast<float4*>(red) + (size_t)(hf * 16) * P4V_TILE + quarter * 32 + lane;
+    while (next_frag(P, sched, f)) {
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads));   // previous fragment done with the tables
+      {
+        const int sg0 = (P.sg_mode == P4V_SG_COLUMN) ? f.tn * P4V_TILE_CG : (f.p % P.nsg);
+        const int sgs = (P.sg_mode == P4V_SG_COLUMN) ? 1 : 0;
+        for (int i = et; i < P.n_fixed_groups * P4V_TILE_CG; i += kEpiThreads)
+          S.fixs[i >> 3][i & 7] = P.fix_scale[(size_t)(i >> 3) * P.nsg + sg0 + (i & 7) * sgs];
+        for (int i = et; i < P.n_cand_groups * P4V_TILE_CG; i += kEpiThreads)
+          S.candB[i >> 3][i & 7] = P.candB[(size_t)(i >> 3) * P.nsg + sg0 + (i & 7) * sgs];
+        for (int i = et + f.c0 * P4V_TILE_CG; i < f.c1 * P4V_TILE_CG; i += kEpiThreads)
+          S.candA[i >> 3][i & 7] = P.candA[(size_t)(i >> 3) * P.nsg + sg0 + (i & 7) * sgs];
+      }
+      {   // residual target into registers, gradient tile (scaled) into this thread's shared-memory row
+        const int gm = f.tm * P4V_TILE + quarter * 32 + lane;
+        const int col0 = f.tn * P4V_TILE + hf * 64;
+        const float* yrow = P.Y + (size_t)f.p * P.prob_stride + (size_t)gm * P.ld;
+        const float* grow = P.Gr + (size_t)f.p * P.prob_stride + (size_t)gm * P.ld;
+        const bool row_ok = gm < P.M;
+        if (P.out != nullptr && !P.out_residual) {           // quant_forward: r starts at -bias, output = -r
+#pragma unroll
+          for (int j = 0; j < 64; ++j) r[j] = (P.bias && col0 + j < P.N) ? -P.bias[col0 + j] : 0.f;
+        } else if (row_ok && (P.ld & 3) == 0 && col0 + 64 <= P.N) {
+#pragma unroll
+          for (int j = 0; j < 64; j += 4) {
+            const float4 yv = *reinterpret_cast<const float4*>(yrow + col0 + j);
+            const float4 bv = P.bias ? *reinterpret_cast<const float4*>(P.bias + col0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            r[j] = yv.x - bv.x; r[j + 1] = yv.y - bv.y; r[j + 2] = yv.z - bv.z; r[j + 3] = yv.w - bv.w;
+            if (P.out == nullptr) {
+              const float4 gv = *reinterpret_cast<const float4*>(grow + col0 + j);
+              gp[(j >> 2) * P4V_TILE] = make_float4(gv.x * gs, gv.y * gs, gv.z * gs, gv.w * gs);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 64; j += 4) {
+            float gq[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int col = col0 + j + k;
+              const bool ok = row_ok && col < P.N;
+              r[j + k] = ok ? (yrow[col] - (P.bias ? P.bias[col] : 0.f)) : 0.f;
+              gq[k] = (ok && P.out == nullptr) ? grow[col] * gs : 0.f;
+            }
+            if (P.out == nullptr) gp[(j >> 2) * P4V_TILE] = make_float4(gq[0], gq[1], gq[2], gq[3]);
+          }
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads));   // tables visible
+      float p[4] = {0.f, 0.f, 0.f, 0.f};
+      if (P.n_fixed_groups > 0) {
+        accm_begin(S, ring, tbase, a0);
+        for (int gi = 0; gi < P.n_fixed_groups; ++gi) {
+          const float4 sc = *reinterpret_cast<const float4*>(&S.fixs[gi][hf * 4]);
+          accm_step<kInt8, false, kPacked>(S, ring, tbase, lane, a0, a1, r, gp, sc, p, gi + 1 < P.n_fixed_groups, dbg2);
+        }
+      }
+      if (P.out != nullptr) {
+        const int gm = f.tm * P4V_TILE + quarter * 32 + lane;
+        const int col0 = f.tn * P4V_TILE + hf * 64;
+        if (gm < P.M) {
+          float* orow = P.out + (size_t)f.p * P.prob_stride + (size_t)gm * P.ld;
+#pragma unroll
+          for (int j = 0; j < 64; ++j) if (col0 + j < P.N) orow[col0 + j] = P.out_residual ? r[j] : -r[j];
+        }
+        continue;
+      }
+      float* part_base = P.partial + ((size_t)f.tile * P.n_cand) * 32 + quarter * 8 + hf * 4;
+      // park the residual target in TMEM columns [0,128); every candidate starts from it
+      tmem_st32(tstore, r);
+      tmem_st32(tstore + 32, r + 32);
+      tmem_wait_st();
+      for (int c = f.c0; c < f.c1; ++c) {
+        const float4 ca = *reinterpret_cast<const float4*>(&S.candA[c][hf * 4]);
+        tmem_ld32f(tstore, r);
+        tmem_ld32f(tstore + 32, r + 32);
+        tmem_wait_ld();
+        accm_begin(S, ring, tbase, a0);
+        for (int gi = 0; gi < P.n_cand_groups; ++gi) {
+          const float4 cb = *reinterpret_cast<const float4*>(&S.candB[gi][hf * 4]);
+          const bool noA = (P.cand_noA_mask >> gi) & 1ull;
+          const float4 sc = noA ? cb : make_float4(ca.x * cb.x, ca.y * cb.y, ca.z * cb.z, ca.w * cb.w);
+          if (ew == 0) TRACE(2, tev, 0);
+          if (gi == P.n_cand_groups - 1) accm_step<kInt8, true, kPacked>(S, ring, tbase, lane, a0, a1, r, gp, sc, p, false, dbg2);
+          else accm_step<kInt8, false, kPacked>(S, ring, tbase, lane, a0, a1, r, gp, sc, p, true, dbg2);
+          if (ew == 0) { TRACE(2, tev, 1); ++tev; }
+        }
+        const float tot = reduce4_over_rows(p[0], p[1], p[2], p[3], lane);
+        if ((lane & 7) == 0) part_base[(size_t)c * 32 + (lane >> 3)] = tot;
+      }
+    }
+    } else {
+    // ---------------- one accumulator per candidate ----------------
     float r[64], g[64];
     uint32_t a0[16], a1[16];
 
@@ -571,7 +830,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
         acc_begin(S, ring, tbase, a0);
         for (int gi = 0; gi < P.n_fixed_groups; ++gi) {
           const float4 sc = *reinterpret_cast<const float4*>(&S.fixs[gi][hf * 4]);
-          acc_step<kInt8, false, kPacked>(S, ring, tbase, lane, a0, a1, r, g, sc, pdummy, gi + 1 < P.n_fixed_groups);
+          acc_step<kInt8, false, kPacked>(S, ring, tbase, lane, a0, a1, r, g, sc, pdummy, gi + 1 < P.n_fixed_groups, dbg2);
         }
       }
       if (P.out != nullptr) {
@@ -585,46 +844,48 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
         continue;
       }
       float* part_base = P.partial + ((size_t)f.tile * P.n_cand) * 32 + quarter * 8 + hf * 4;
+      [[maybe_unused]] float* const part_base_tile = P.partial + ((size_t)f.tile * P.n_cand) * 32;
 
-      if constexpr (kSingle) {
+      {
         // -- one accumulator per candidate --
         if (f.c1 > f.c0) acc_begin(S, ring, tbase, a0);
         const float4 cb = *reinterpret_cast<const float4*>(&S.candB[0][hf * 4]);
         const bool noA = P.cand_noA_mask & 1ull;
+        // my slot in the reduction buffers (writer) and my (candidate, row quarter, group) task (reader)
+        float* const red_w = red + hf * kRedHalf + (quarter * 32 + lane) * 4;
+        const int rd_j = et >> 5, rd_q = (et >> 3) & 3, rd_g = et & 7;
+        const float* const red_r = red + rd_j * kRedCand + (rd_g >> 2) * kRedHalf + (rd_q * 32) * 4 + (rd_g & 3);
+        int nb = 0, buf = 0;
         for (int c = f.c0; c < f.c1; ++c) {
           float p[4];
+          if (ew == 0) TRACE(2, tev, 0);
           const float4 ca = *reinterpret_cast<const float4*>(&S.candA[c][hf * 4]);
           const float4 sc = noA ? cb : make_float4(ca.x * cb.x, ca.y * cb.y, ca.z * cb.z, ca.w * cb.w);
-          acc_step<kInt8, true, kPacked>(S, ring, tbase, lane, a0, a1, r, g, sc, p, c + 1 < f.c1);
-          const float tot = reduce4_over_rows(p[0], p[1], p[2], p[3], lane);
-          if ((lane & 7) == 0) part_base[(size_t)c * 32 + (lane >> 3)] = tot;
-        }
-      } else {
-        // -- several segments per candidate: park the residual target in TMEM columns [0,128) --
-        tmem_st32(tstore, r);
-        tmem_st32(tstore + 32, r + 32);
-        tmem_wait_st();
-        for (int c = f.c0; c < f.c1; ++c) {
-          const float4 ca = *reinterpret_cast<const float4*>(&S.candA[c][hf * 4]);
-          float p[4] = {0.f, 0.f, 0.f, 0.f};
-          tmem_ld32f(tstore, r);
-          tmem_ld32f(tstore + 32, r + 32);
-          tmem_wait_ld();
-          acc_begin(S, ring, tbase, a0);
-          for (int gi = 0; gi < P.n_cand_groups; ++gi) {
-            const float4 cb = *reinterpret_cast<const float4*>(&S.candB[gi][hf * 4]);
-            const bool noA = (P.cand_noA_mask >> gi) & 1ull;
-            const float4 sc = noA ? cb : make_float4(ca.x * cb.x, ca.y * cb.y, ca.z * cb.z, ca.w * cb.w);
-            if (gi == P.n_cand_groups - 1) acc_step<kInt8, true, kPacked>(S, ring, tbase, lane, a0, a1, r, g, sc, p, false);
-            else acc_step<kInt8, false, kPacked>(S, ring, tbase, lane, a0, a1, r, g, sc, p, true);
+          acc_step<kInt8, true, kPacked>(S, ring, tbase, lane, a0, a1, r, g, sc, p, c + 1 < f.c1, dbg2);
+          if (ew == 0) TRACE(2, tev, 1);
+          *reinterpret_cast<float4*>(red_w + (buf * kRedBatch + nb) * kRedCand) = make_float4(p[0], p[1], p[2], p[3]);
+          if (ew == 0) TRACE(2, tev, 2);
+          if (++nb == kRedBatch || c + 1 == f.c1) {
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads));
+            if (rd_j < nb) {                       // sum 32 rows; the start row is rotated per quarter (bank spread)
+              const float* src = red_r + buf * kRedBatch * kRedCand;
+              float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                t0 += src[((i + 2 * rd_q) & 31) * 4];
+                t1 += src[((i + 1 + 2 * rd_q) & 31) * 4];
+              }
+              part_base_tile[(size_t)(c + 1 - nb + rd_j) * 32 + (et & 31)] = t0 + t1;
+            }
+            buf ^= 1; nb = 0;
           }
-          const float tot = reduce4_over_rows(p[0], p[1], p[2], p[3], lane);
-          if ((lane & 7) == 0) part_base[(size_t)c * 32 + (lane >> 3)] = tot;
+          if (ew == 0) { TRACE(2, tev, 3); ++tev; }
         }
       }
     }
   }
 
+    }
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
@@ -635,6 +896,10 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
 }
 
 }  // namespace
+
+// debug hook (not part of the public header): 1 = no operand traffic / MMA, 2 = no epilogue math; initialised from P4V_SWEEP_DEBUG
+static int g_sweep_debug = [] { const char* e = getenv("P4V_SWEEP_DEBUG"); return e ? atoi(e) : 0; }();
+extern "C" __attribute__((visibility("default"))) int p4v_debug_sweep_mode(int mode) { g_sweep_debug = mode; return 0; }
 
 int p4v_launch_sweep_tc(const SweepParams& p_in, const P4VJob* host_jobs, int num_sms, cudaStream_t st) {
   SweepParams p = p_in;
@@ -649,28 +914,40 @@ int p4v_launch_sweep_tc(const SweepParams& p_in, const P4VJob* host_jobs, int nu
   if (grid < 1) return 0;
   // smem plan: stage size = largest job; resident row operand when the host marked the candidate jobs P4V_JOB_RRES
   uint32_t max_kb = 32, res_bytes = 0;
-  bool any_r_stream = false;
+  bool any_r_stream = false, any_c_stream = false, any_cres = false;
   for (int j = 0; j < n_jobs; ++j) {
-    if (host_jobs[j].kb > max_kb) max_kb = host_jobs[j].kb;
-    if (host_jobs[j].flags & P4V_JOB_RRES) res_bytes = std::max(res_bytes, host_jobs[j].res_off + (uint32_t)host_jobs[j].kb * P4V_TILE);
+    const uint32_t kb_total = host_jobs[j].kb * p4v_job_nsub(host_jobs[j]);
+    P4V_REQUIRE(host_jobs[j].kb % 32 == 0 && kb_total >= 32 && kb_total <= P4V_JOB_KB, "sweep: bad job size");
+    if (kb_total > max_kb) max_kb = kb_total;
+    if (host_jobs[j].flags & P4V_JOB_RRES) res_bytes = std::max(res_bytes, host_jobs[j].res_off + kb_total * P4V_TILE);
     else any_r_stream = true;
+    if (host_jobs[j].flags & P4V_JOB_CRES) any_cres = true; else any_c_stream = true;
   }
   p.stage_r_bytes = any_r_stream ? max_kb * P4V_TILE : 0;
-  p.stage_c_bytes = max_kb * P4V_TILE;
+  p.stage_c_bytes = any_c_stream ? max_kb * P4V_TILE : 0;
   p.resident_bytes = res_bytes;
+  p.cres_bytes = any_cres ? (unsigned int)p.C_tile_bytes : 0;
+  P4V_REQUIRE(p.cres_bytes % 16 == 0 && p.cres_bytes <= 128 * 1024, "sweep: resident column image too large");
   const uint32_t per_stage = p.stage_r_bytes + p.stage_c_bytes;
-  int nst = (int)((kSmemBudget - 2 * (long long)res_bytes) / per_stage);
+  P4V_REQUIRE(per_stage > 0, "sweep: no streamed operand");
+  const bool single = p.n_cand_groups == 1 && p.out == nullptr;
+  const long long red_bytes = single ? kRedBytes : (p.out == nullptr ? (long long)P4V_TILE * P4V_TILE * 4 : 0);   // score reduction buffers / parked gradient tile
+  p.resident_bufs = 2;                      // double buffered when that leaves a useful ring, else one buffer (a bubble per tile)
+  if ((kSmemBudget - 2 * (long long)res_bytes - red_bytes - (long long)p.cres_bytes) / per_stage < 3) p.resident_bufs = 1;
+  int nst = (int)((kSmemBudget - (long long)p.resident_bufs * res_bytes - red_bytes - (long long)p.cres_bytes) / per_stage);
   if (nst > kMaxStages) nst = kMaxStages;
   P4V_REQUIRE(nst >= 2, "sweep: operand tiles do not fit the shared-memory ring");
   p.n_stages = nst;
-  const size_t smem = (size_t)nst * per_stage + 2 * (size_t)res_bytes + sizeof(SmemCtl) + 256;
-  const bool single = p.n_cand_groups == 1 && p.out == nullptr;
+  const size_t smem = (size_t)nst * per_stage + (size_t)p.resident_bufs * res_bytes + p.cres_bytes + ((sizeof(SmemCtl) + 127) & ~size_t(127)) + (size_t)red_bytes + 256;
 #define P4V_LAUNCH(I8, SG, PK)                                                                         \
   do {                                                                                                 \
     P4V_CUDA_OK(cudaFuncSetAttribute(sweep_tc_kernel<I8, SG, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     sweep_tc_kernel<I8, SG, PK><<<grid, kThreads, smem, st>>>(p);                                      \
   } while (0)
 #define P4V_LAUNCH2(I8, SG) do { if (packed) P4V_LAUNCH(I8, SG, true); else P4V_LAUNCH(I8, SG, false); } while (0)
+  p.debug_mode = g_sweep_debug;
+  static const int mma_warps = [] { const char* e = getenv("P4V_MMA_WARPS"); return (e && atoi(e) == 2) ? 2 : 1; }();   // 2 = experimental second issuer warp
+  p.mma_warps = mma_warps;
   static const bool packed = [] { const char* e = getenv("P4V_PACKED"); return e ? atoi(e) != 0 : true; }();
   if (p.is_int8) { if (single) P4V_LAUNCH2(true, true); else P4V_LAUNCH2(true, false); }
   else           { if (single) P4V_LAUNCH2(false, true); else P4V_LAUNCH2(false, false); }

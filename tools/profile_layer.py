@@ -34,3 +34,12 @@ with torch.no_grad():
     run(); torch.cuda.synchronize()
     t0 = time.time(); run(); torch.cuda.synchronize()
 print(f"{kind} rounds={rounds} blocks={nb}: {1e3 * (time.time() - t0):.2f} ms")
+if os.environ.get("P4V_PROFILE_LOG"):
+    import ctypes as C
+    from ptq4vit_b200._lib import lib
+    L = lib(); L.p4v_profile_enable(1)
+    with torch.no_grad():
+        run(); torch.cuda.synchronize()
+    ms, n, ops = C.c_double(), C.c_longlong(), C.c_double()
+    L.p4v_profile_collect(C.byref(ms), C.byref(n), C.byref(ops))
+    print(f"sweep launches {n.value}, {ms.value:.3f} ms total, {ops.value / ms.value / 1e9:.1f} TFLOP/s executed")

@@ -36,17 +36,18 @@ lib.p4v_debug_trace(None)
 t = tr.cpu().numpy().reshape(3, 512, 4)
 t0 = t[1, 0, 0]
 np.save(os.path.join(ROOT, "gpurun_out", f"trace_{kind}.npy"), t)
-def show(role, name, cols):
+def show(role, name, cols, rng=None):
     print(name)
-    for i in list(range(0, 40)) + list(range(200, 216)):
+    for i in (rng or (list(range(0, 12)) + list(range(60, 100)))):
         e = t[role, i]
         if e[0] == 0: break
-        print(i, [int(v - t0) if k < cols else int(v) for k, v in enumerate(e)])
-show(0, "producer: [t_before_wait_empty, t_after, stage, cand]", 2)
+        print(i, [int(v - t0) if k < cols else int(v) for k, v in enumerate(e)], "d:", [int(e[k + 1] - e[k]) for k in range(cols - 1)],
+              "period:", int(e[0] - t[role, i - 1, 0]) if i else 0)
+show(0, "producer: [t_before_wait_empty, t_after_wait, t_after_issue]", 3)
 show(1, "mma: [t_start, t_after_acc_empty, t_after_full, t_end]", 4)
-show(2, "epilogue w4: [t_start, t_after_release, t_after_next_full+ld_issue, t_end]", 4)
-for role, nm in ((1, "mma"), (2, "epi")):
+show(2, "epilogue w4: [t_start, t_after_acc_step(release+next full), t_after_reduce, t_after_store]", 4)
+for role, nm in ((0, "prod"), (1, "mma"), (2, "epi")):
     v = t[role]; k = int((v[:, 0] != 0).sum())
     if k > 60:
-        per = (v[k - 1, 3] - v[40, 0]) / (k - 41)
+        per = (v[k - 1, 0] - v[40, 0]) / (k - 41)
         print(nm, "events", k, "avg cycles per event (steady)", per)
