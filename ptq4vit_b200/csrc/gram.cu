@@ -44,22 +44,23 @@ __global__ void xq_transpose_kernel(const float* __restrict__ x, int M, int K, i
   }
 }
 
-// Z image: rows = pairs (k <= k') of the slab, K = tokens; value = Xq[m,k] * Xq[m,k'] split exactly into two bf16 terms.
-// image layout [tile][chunk][128][16 B] ; hi term at byte offset 0 of the padded row, lo term at term_bytes.
-__global__ void pair_image_kernel(const int8_t* __restrict__ XqT, int Mp, int M, int k_first, int ks, int npairs,
+// Z image: rows = (column block, pair k <= k' of the block), K = tokens; value = Xq[m,k] * Xq[m,k'] split exactly into two
+// bf16 terms.  Layout [tile of 256 rows][chunk][256][16 B]; hi term at byte offset 0 of the padded row, lo term at term_bytes.
+__global__ void pair_image_kernel(const int8_t* __restrict__ XqT, int Mp, int M, int k_first, int ks, int npairs, int n_blocks,
                                   int tiles_p, unsigned long long tile_bytes, unsigned int term_bytes, uint8_t* __restrict__ dst) {
-  const int rows_pad = tiles_p * P4V_TILE;
-  const int row = blockIdx.x * blockDim.x + threadIdx.x;        // pair index (padded)
+  const int rows_pad = tiles_p * GRAM_PT;
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;        // (block, pair) index (padded)
   const int chunk = blockIdx.y;                                  // 8 tokens
   if (row >= rows_pad) return;
   uint32_t hi[4] = {0, 0, 0, 0}, lo[4] = {0, 0, 0, 0};
-  if (row < npairs) {
+  if (row < npairs * n_blocks) {
+    const int blk = row / npairs, pr = row % npairs;
     // invert p = k*ks - k(k-1)/2 + (k' - k)
     int k = 0, base = 0;
-    while (base + (ks - k) <= row) { base += ks - k; ++k; }
-    const int k2 = k + (row - base);
-    const int8_t* a = XqT + (size_t)(k_first + k) * Mp + chunk * 8;
-    const int8_t* b = XqT + (size_t)(k_first + k2) * Mp + chunk * 8;
+    while (base + (ks - k) <= pr) { base += ks - k; ++k; }
+    const int k2 = k + (pr - base);
+    const int8_t* a = XqT + (size_t)(k_first + blk * ks + k) * Mp + chunk * 8;
+    const int8_t* b = XqT + (size_t)(k_first + blk * ks + k2) * Mp + chunk * 8;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int m = chunk * 8 + e;
@@ -70,10 +71,10 @@ __global__ void pair_image_kernel(const int8_t* __restrict__ XqT, int Mp, int M,
       lo[e >> 1] |= (uint32_t)__bfloat16_as_ushort(l) << ((e & 1) * 16);
     }
   }
-  const int tile = row / P4V_TILE, r = row % P4V_TILE;
-  uint8_t* base_p = dst + (size_t)tile * tile_bytes + ((size_t)chunk * P4V_TILE + r) * 16;
+  const int tile = row / GRAM_PT, r = row % GRAM_PT;
+  uint8_t* base_p = dst + (size_t)tile * tile_bytes + ((size_t)chunk * GRAM_PT + r) * 16;
   *reinterpret_cast<uint4*>(base_p) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-  *reinterpret_cast<uint4*>(base_p + (size_t)term_bytes * P4V_TILE) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  *reinterpret_cast<uint4*>(base_p + (size_t)term_bytes * GRAM_PT) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
 // One pass over e and g: apply the rank-ks update of the previous step, accumulate U and sum (g e)^2 for the next slab.
@@ -286,10 +287,10 @@ int p4v_xq_transpose(const float* x, int M, int K, int Mp, const float* dX, int 
   return 0;
 }
 
-int p4v_pair_image(const int8_t* XqT, int Mp, int M, int k_first, int ks, int npairs, int tiles_p, unsigned long long tile_bytes,
-                   unsigned int term_bytes, uint8_t* dst, cudaStream_t st) {
-  dim3 grid(tiles_p, term_bytes / 16);
-  pair_image_kernel<<<grid, 128, 0, st>>>(XqT, Mp, M, k_first, ks, npairs, tiles_p, tile_bytes, term_bytes, dst); p4v_count_launch();
+int p4v_pair_image(const int8_t* XqT, int Mp, int M, int k_first, int ks, int npairs, int n_blocks, int tiles_p,
+                   unsigned long long tile_bytes, unsigned int term_bytes, uint8_t* dst, cudaStream_t st) {
+  dim3 grid(tiles_p * (GRAM_PT / 128), term_bytes / 16);
+  pair_image_kernel<<<grid, 128, 0, st>>>(XqT, Mp, M, k_first, ks, npairs, n_blocks, tiles_p, tile_bytes, term_bytes, dst); p4v_count_launch();
   P4V_CUDA_OK(cudaGetLastError());
   return 0;
 }

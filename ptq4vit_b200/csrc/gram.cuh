@@ -34,5 +34,16 @@ int p4v_gram_eval(const GramEvalArgs& a, cudaStream_t st);
 int p4v_gram_reduce(const float* Upart, const float* E2part, int n_mblk, int O, int ks, float* U, float* E2, cudaStream_t st);
 
 int p4v_xq_transpose(const float* x, int M, int K, int Mp, const float* dX, int crb_acts, float qlo, float qhi, int8_t* out, cudaStream_t st);
-int p4v_pair_image(const int8_t* XqT, int Mp, int M, int k_first, int ks, int npairs, int tiles_p, unsigned long long tile_bytes,
-                   unsigned int term_bytes, uint8_t* dst, cudaStream_t st);
+// Z image of n_blocks column blocks starting at weight column k_first: row (b * npairs + pair) of 256-row tiles
+int p4v_pair_image(const int8_t* XqT, int Mp, int M, int k_first, int ks, int npairs, int n_blocks, int tiles_p,
+                   unsigned long long tile_bytes, unsigned int term_bytes, uint8_t* dst, cudaStream_t st);
+
+#define GRAM_PT 256      // pair rows per tile of the Z image (= N of the Gram GEMM's MMA)
+struct GramGemmArgs {
+  const uint8_t* R; unsigned long long R_tile_bytes;   // (gs*g)^2 image: [tiles_o][2 terms][K chunk][128][16 B]
+  const uint8_t* C; unsigned long long C_tile_bytes;   // pair image:     [tiles_p][2 terms][K chunk][256][16 B]
+  unsigned int term_bytes;                             // bytes of K (tokens * 2, padded to 32) of one term
+  int tiles_o, tiles_p, O;
+  float* H; long long ldH;                             // [O][ldH], ldH >= tiles_p * 256
+};
+int p4v_gram_gemm(const GramGemmArgs& a, cudaStream_t st);

@@ -112,9 +112,8 @@ struct LinPlan {
   std::vector<Step> wsteps, xsteps;
   Step fwd;   // quant_forward: every segment is a fixed group
   // normal-equation W search (gram.cu)
-  bool gram; int g_ks, g_Mp, g_npairs, g_tiles_p, g_ldH, g_nmblk, g_njobs; unsigned g_term_bytes;
-  std::vector<P4VJob> gjobs;
-  size_t o_E, o_XqT, o_G2T, o_Z, o_H, o_Upart, o_E2part, o_U, o_E2, o_dprev, o_ones, o_gjobs, o_segsG;
+  bool gram; int g_ks, g_Mp, g_npairs, g_tiles_p, g_ldH, g_nmblk; unsigned g_term_bytes;
+  size_t o_E, o_XqT, o_G2T, o_Z, o_H, o_Upart, o_E2part, o_U, o_E2, o_dprev, o_segsG;
   int g_osplit, g_opb;
   std::vector<float> factors;
   int max_groups;
@@ -338,39 +337,24 @@ int build_plan(const p4v_linear_desc* d, LinPlan& p, bool with_search) {
     const char* env = getenv("P4V_GRAM");
     const bool want = with_search && (env ? atoi(env) != 0 : true) && d->kernel == P4V_KERNEL_TCGEN05;
     const unsigned term = (unsigned)align_up((size_t)p.M * 2, 32);
-    const int nj = (int)((term + P4V_JOB_KB - 1) / P4V_JOB_KB);
-    if (want && !p.twin && p.crb_cols <= 64 && p.crb_cols % 4 == 0 && p.crb_acts % p.crb_cols == 0 && 3 * nj <= P4V_MAX_JOBS) {
+    if (want && !p.twin && p.crb_cols <= 64 && p.crb_cols % 4 == 0 && p.crb_acts % p.crb_cols == 0) {
       p.gram = true;
-      p.g_ks = p.crb_cols; p.g_term_bytes = term; p.g_njobs = nj;
+      p.g_ks = p.crb_cols; p.g_term_bytes = term;
       p.g_Mp = (int)align_up((size_t)p.M, 16) + 16;
       p.g_npairs = p.g_ks * (p.g_ks + 1) / 2;
-      p.g_tiles_p = p4v_cdiv(p.g_npairs, P4V_TILE); p.g_ldH = p.g_tiles_p * P4V_TILE;
+      p.g_tiles_p = p4v_cdiv(p.g_npairs * d->n_H, GRAM_PT); p.g_ldH = p.g_tiles_p * GRAM_PT;   // all column blocks side by side
       p.g_nmblk = p4v_cdiv(p.M, GRAM_BM);
-      p.gjobs.clear();
-      const int combos[3][2] = {{0, 0}, {0, 1}, {1, 0}};          // (g^2 term, Z term): hi*hi + hi*lo + lo*hi
-      for (int gi = 0; gi < 3; ++gi)
-        for (int j = 0; j < nj; ++j) {
-          P4VJob jb{};
-          const unsigned b = (unsigned)j * P4V_JOB_KB;
-          jb.r_off = (combos[gi][0] * term + b) * P4V_TILE; jb.c_off = (combos[gi][1] * term + b) * P4V_TILE;
-          jb.kb = (uint8_t)std::min<unsigned>(P4V_JOB_KB, term - b);
-          jb.flags = (j == 0 ? P4V_JOB_FIRST : 0) | (j == nj - 1 ? P4V_JOB_LAST : 0);
-          jb.group = (uint8_t)gi;
-          p.gjobs.push_back(jb);
-        }
       const size_t KBg = 2 * (size_t)term;
       p.o_E = take((size_t)p.M * p.O * 4);
       p.o_XqT = take((size_t)p.K * p.g_Mp);
       p.o_G2T = take((size_t)p.tiles_o * P4V_TILE * KBg);
-      p.o_Z = take((size_t)p.g_tiles_p * P4V_TILE * KBg);
+      p.o_Z = take((size_t)p.g_tiles_p * GRAM_PT * KBg);
       p.o_H = take((size_t)p.O * p.g_ldH * 4);
       p.o_Upart = take((size_t)p.g_nmblk * p.O * p.g_ks * 4);
       p.o_E2part = take((size_t)p.g_nmblk * p.O * 4);
       p.o_U = take((size_t)p.O * p.g_ks * 4); p.o_E2 = take((size_t)p.O * 4);
       p.g_osplit = std::max(1, p4v_cdiv(p.crb_rows, 2)); p.g_opb = p4v_cdiv(p.crb_rows, p.g_osplit);
       p.o_dprev = take((size_t)d->n_V * 4);
-      p.o_ones = take((size_t)3 * p.g_tiles_p * P4V_TILE_CG * 4);
-      p.o_gjobs = take(p.gjobs.size() * sizeof(P4VJob));
       p.o_segsG = take(2 * sizeof(P4VSeg));
     }
   }
@@ -390,9 +374,6 @@ int upload_tables(const LinPlan& p, void* ws, cudaStream_t st) {
   if (!p.commits.empty())
     P4V_CUDA_OK(cudaMemcpyAsync(at<void>(ws, p.o_commits), p.commits.data(), p.commits.size() * sizeof(CommitSeg), cudaMemcpyHostToDevice, st));
   if (p.gram) {
-    P4V_CUDA_OK(cudaMemcpyAsync(at<void>(ws, p.o_gjobs), p.gjobs.data(), p.gjobs.size() * sizeof(P4VJob), cudaMemcpyHostToDevice, st));
-    std::vector<float> ones((size_t)3 * p.g_tiles_p * P4V_TILE_CG, 1.f);
-    P4V_CUDA_OK(cudaMemcpyAsync(at<void>(ws, p.o_ones), ones.data(), ones.size() * 4, cudaMemcpyHostToDevice, st));
     P4VSeg sg[2] = {{0, p.M, 0, 0, 0.f, 0.f, 0.f, 0, 0.f, 1, 1}, {0, p.M, (int)(p.g_term_bytes * P4V_TILE), 0, 0.f, 0.f, 0.f, 0, 0.f, 2, 1}};
     P4V_CUDA_OK(cudaMemcpyAsync(at<void>(ws, p.o_segsG), sg, sizeof(sg), cudaMemcpyHostToDevice, st));
   }
@@ -524,7 +505,20 @@ int gram_wsearch(const LinPlan& p, void* ws, const float* x, const float* W, con
   }
   if ((rc = p4v_xq_transpose(x, p.M, p.K, p.g_Mp, at<float>(ws, p.o_dX), p.crb_acts, (float)-p.a_qmax, (float)(p.a_qmax - 1),
                              at<int8_t>(ws, p.o_XqT), st))) return rc;
-  const unsigned long long tile_bytes = (unsigned long long)P4V_TILE * 2 * p.g_term_bytes;
+  // H for every column block of the range: one pair image + one tensor-core GEMM (the activations do not change
+  // during the weight steps of a round)
+  {
+    const int nblk = h_end - h_begin;
+    const unsigned long long z_tile = (unsigned long long)GRAM_PT * 2 * p.g_term_bytes;
+    const int tiles_p = p4v_cdiv(p.g_npairs * nblk, GRAM_PT);
+    if ((rc = p4v_pair_image(at<int8_t>(ws, p.o_XqT), p.g_Mp, p.M, h_begin * p.g_ks, p.g_ks, p.g_npairs, nblk, tiles_p, z_tile,
+                             p.g_term_bytes, at<uint8_t>(ws, p.o_Z), st))) return rc;
+    GramGemmArgs gg{};
+    gg.R = at<uint8_t>(ws, p.o_G2T); gg.R_tile_bytes = (unsigned long long)P4V_TILE * 2 * p.g_term_bytes;
+    gg.C = at<uint8_t>(ws, p.o_Z); gg.C_tile_bytes = z_tile; gg.term_bytes = p.g_term_bytes;
+    gg.tiles_o = p.tiles_o; gg.tiles_p = tiles_p; gg.O = p.O; gg.H = at<float>(ws, p.o_H); gg.ldH = p.g_ldH;
+    if ((rc = p4v_gram_gemm(gg, st))) return rc;
+  }
   for (int h = h_begin; h < h_end; ++h) {
     GramUpdateArgs u{};
     u.E = at<float>(ws, p.o_E); u.G = g; u.gscale = at<float>(ws, p.o_gscale);
@@ -534,22 +528,8 @@ int gram_wsearch(const LinPlan& p, void* ws, const float* x, const float* W, con
     u.h_prev = h > h_begin ? h - 1 : -1; u.k_prev = (h - 1) * p.g_ks; u.k_next = h * p.g_ks; u.ks = p.g_ks;
     u.w_lo = w_lo; u.w_hi = w_hi; u.Upart = at<float>(ws, p.o_Upart); u.E2part = at<float>(ws, p.o_E2part);
     if ((rc = p4v_gram_update(u, st))) return rc;
-    if ((rc = p4v_pair_image(at<int8_t>(ws, p.o_XqT), p.g_Mp, p.M, h * p.g_ks, p.g_ks, p.g_npairs, p.g_tiles_p, tile_bytes,
-                             p.g_term_bytes, at<uint8_t>(ws, p.o_Z), st))) return rc;
-    {
-      SweepParams sp{};
-      sp.R_cur = at<uint8_t>(ws, p.o_G2T); sp.C_cur = at<uint8_t>(ws, p.o_Z);
-      sp.R_tile_bytes = sp.C_tile_bytes = tile_bytes;
-      sp.P = 1; sp.M = p.O; sp.N = p.g_ldH; sp.tiles_m = p.tiles_o; sp.tiles_n = p.g_tiles_p;
-      sp.ld = p.g_ldH; sp.prob_stride = 0; sp.gscale = at<float>(ws, p.o_gscale);
-      sp.jobs = at<P4VJob>(ws, p.o_gjobs); sp.n_fixed_jobs = (int)p.gjobs.size(); sp.n_fixed_groups = 3;
-      sp.fix_scale = at<float>(ws, p.o_ones); sp.candA = sp.fix_scale; sp.candB = sp.fix_scale;
-      sp.nsg = p.g_tiles_p * P4V_TILE_CG; sp.sg_mode = P4V_SG_COLUMN;
-      sp.n_cand = 1; sp.out = at<float>(ws, p.o_H); sp.order = 0; sp.is_int8 = 0;
-      if ((rc = p4v_run_sweep(sp, p.gjobs.data(), p.d.kernel, st))) return rc;
-    }
     GramEvalArgs ev{};
-    ev.H = at<float>(ws, p.o_H); ev.ldH = p.g_ldH; ev.npairs = p.g_npairs;
+    ev.H = at<float>(ws, p.o_H) + (size_t)(h - h_begin) * p.g_npairs; ev.ldH = p.g_ldH; ev.npairs = p.g_npairs;
     if ((rc = p4v_gram_reduce(u.Upart, u.E2part, p.g_nmblk, p.O, p.g_ks, at<float>(ws, p.o_U), at<float>(ws, p.o_E2), st))) return rc;
     ev.U = at<float>(ws, p.o_U); ev.E2 = at<float>(ws, p.o_E2);
     ev.W = W; ev.O = p.O; ev.K = p.K; ev.k_first = h * p.g_ks; ev.ks = p.g_ks;
