@@ -77,120 +77,141 @@ __global__ void pair_image_kernel(const int8_t* __restrict__ XqT, int Mp, int M,
   *reinterpret_cast<uint4*>(base_p + (size_t)term_bytes * GRAM_PT) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
+// packed fp32x2 math (sm_100): one issue slot per two FMAs
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+
+// D[o][k] = what the previous step's pick changed in the quantised weights of its column block (ks numbers per channel)
+__global__ void gram_delta_kernel(const float* __restrict__ W, int O, int K, int k_prev, int ks, int ldD,
+                                  const float* __restrict__ dW, const float* __restrict__ dW_prev, int n_V, int n_H, int crb_rows,
+                                  int h_prev, float w_lo, float w_hi, float* __restrict__ D) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= O * ldD) return;
+  const int o = i / ldD, k = i % ldD;
+  float v = 0.f;
+  if (k < ks) {
+    const int vb = min(o / crb_rows, n_V - 1);
+    const float w = W[(size_t)o * K + k_prev + k];
+    v = fq_dev(w, dW[vb * n_H + h_prev], w_lo, w_hi) - fq_dev(w, dW_prev[vb], w_lo, w_hi);
+  }
+  D[i] = v;
+}
+
 // One pass over e and g: apply the rank-ks update of the previous step, accumulate U and sum (g e)^2 for the next slab.
-// block = 256 output channels x GRAM_BM tokens; thread = TWO output channels (o, o+128): every xhat value fetched from
-// shared memory feeds two FMAs, which halves the shared-memory traffic that otherwise bounds this kernel.
+// grid = (256-channel blocks) x (token splits, sized so that the grid is ONE balanced wave); a block walks its token
+// range in chunks of GRAM_BM tokens and keeps the U accumulators of its channels in registers the whole time, so there
+// is one partial per block.  thread = TWO output channels (o, o+128): every xhat value fetched from shared memory
+// feeds two packed FMAs.
 template <int KS>
 __global__ void __launch_bounds__(128) gram_update_kernel(const GramUpdateArgs a) {
-  extern __shared__ float sm[];
-  float* xp = sm;                       // [BM][KS] previous slab (xhat), only if a.h_prev >= 0
-  float* xn = sm + GRAM_BM * KS;        // [BM][KS] next slab
+  __shared__ __align__(16) float xp[GRAM_BM * KS];       // previous slab (xhat), only if a.h_prev >= 0
+  __shared__ __align__(16) float xn[GRAM_BM * KS];       // next slab
   const int oA = blockIdx.x * 256 + threadIdx.x, oB = oA + 128;
-  const int m0 = blockIdx.y * GRAM_BM;
-  const int rows = min(GRAM_BM, a.M - m0);
+  const bool okA = oA < a.O, okB = oB < a.O;
   const float gs = a.gscale[0];
   const bool has_prev = a.h_prev >= 0;
-  // slab tiles of the token-major int8 activations -> fp32 xhat in shared memory ([token][k], k contiguous).
-  // thread = (k, 16-token chunk): one 16-byte load per slab row segment, conflict-free stores (lanes = consecutive k).
-  for (int it = threadIdx.x; it < KS * (GRAM_BM / 16); it += 128) {
-    const int k = it % KS, ch = it / KS;
-    const int mm0 = ch * 16;
-    float vn[16], vp[16];
+  const int nb16 = (a.M + 15) / 16;                     // split on 16-token boundaries: the slab loads stay 16-byte aligned
+  const int m_begin = (int)((long long)nb16 * blockIdx.y / gridDim.y) * 16;
+  const int m_end = min(a.M, (int)((long long)nb16 * (blockIdx.y + 1) / gridDim.y) * 16);
+  f32x2 dA[KS / 2], dB[KS / 2], accA[KS / 2], accB[KS / 2];
 #pragma unroll
-    for (int e = 0; e < 16; ++e) { vn[e] = 0.f; vp[e] = 0.f; }
-    if (k < a.ks && mm0 < rows) {
-      const float dn = a.dX[(a.k_next + k) / a.crb_acts];
-      const int4 qn = *reinterpret_cast<const int4*>(a.XqT + (size_t)(a.k_next + k) * a.Mp + m0 + mm0);
-      const int8_t* bn = reinterpret_cast<const int8_t*>(&qn);
-#pragma unroll
-      for (int e = 0; e < 16; ++e) vn[e] = (mm0 + e < rows) ? dn * (float)bn[e] : 0.f;
-      if (has_prev) {
-        const float dp = a.dX[(a.k_prev + k) / a.crb_acts];
-        const int4 qp = *reinterpret_cast<const int4*>(a.XqT + (size_t)(a.k_prev + k) * a.Mp + m0 + mm0);
-        const int8_t* bp = reinterpret_cast<const int8_t*>(&qp);
-#pragma unroll
-        for (int e = 0; e < 16; ++e) vp[e] = (mm0 + e < rows) ? dp * (float)bp[e] : 0.f;
-      }
-    }
-#pragma unroll
-    for (int e = 0; e < 16; ++e) { xn[(mm0 + e) * KS + k] = vn[e]; xp[(mm0 + e) * KS + k] = vp[e]; }
-  }
-  float dA[KS], dB[KS], accA[KS], accB[KS];
-#pragma unroll
-  for (int k = 0; k < KS; ++k) { dA[k] = 0.f; dB[k] = 0.f; accA[k] = 0.f; accB[k] = 0.f; }
-  const bool okA = oA < a.O, okB = oB < a.O;
+  for (int k = 0; k < KS / 2; ++k) { dA[k] = 0ull; dB[k] = 0ull; accA[k] = 0ull; accB[k] = 0ull; }
   if (has_prev) {
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      const int o = half ? oB : oA;
-      if (o < a.O) {
-        const int v = min(o / a.crb_rows, a.n_V - 1);
-        const float d_new = a.dW[v * a.n_H + a.h_prev], d_old = a.dW_prev[v];
-        const float* wrow = a.W + (size_t)o * a.K + a.k_prev;
-#pragma unroll
-        for (int k = 0; k < KS; ++k)
-          if (k < a.ks) {
-            const float dl = fq_dev(wrow[k], d_new, a.w_lo, a.w_hi) - fq_dev(wrow[k], d_old, a.w_lo, a.w_hi);
-            if (half) dB[k] = dl; else dA[k] = dl;
-          }
-      }
+    for (int k = 0; k < KS; k += 4) {
+      if (okA) { const float4 v = *reinterpret_cast<const float4*>(a.D + (size_t)oA * KS + k); dA[k / 2] = pack2(v.x, v.y); dA[k / 2 + 1] = pack2(v.z, v.w); }
+      if (okB) { const float4 v = *reinterpret_cast<const float4*>(a.D + (size_t)oB * KS + k); dB[k / 2] = pack2(v.x, v.y); dB[k / 2 + 1] = pack2(v.z, v.w); }
     }
   }
-  __syncthreads();
   float e2A = 0.f, e2B = 0.f;
-  constexpr int UN = 4;                                   // tokens in flight per thread and channel
-  for (int mm0 = 0; mm0 < rows; mm0 += UN) {
-    float eA[UN], gA[UN], eB[UN], gB[UN];
+  for (int m0 = m_begin; m0 < m_end; m0 += GRAM_BM) {
+    const int rows = min(GRAM_BM, m_end - m0);
+    __syncthreads();                                      // previous chunk consumed
+    // slab chunks of the token-major int8 activations -> fp32 xhat in shared memory ([token][k], k contiguous);
+    // thread = (k, 16-token piece): one 16-byte load per slab row piece, conflict-free stores (lanes = consecutive k)
+    for (int it = threadIdx.x; it < KS * (GRAM_BM / 16); it += 128) {
+      const int k = it % KS, mm0 = (it / KS) * 16;
+      float vn[16], vp[16];
 #pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      const bool ok = mm0 + u < rows;
-      const size_t off = (size_t)(m0 + mm0 + u) * a.O;
-      eA[u] = (ok && okA) ? a.E[off + oA] : 0.f; gA[u] = (ok && okA) ? a.G[off + oA] * gs : 0.f;
-      eB[u] = (ok && okB) ? a.E[off + oB] : 0.f; gB[u] = (ok && okB) ? a.G[off + oB] * gs : 0.f;
-    }
+      for (int e = 0; e < 16; ++e) { vn[e] = 0.f; vp[e] = 0.f; }
+      if (k < a.ks && mm0 < rows) {
+        const float dn = a.dX[(a.k_next + k) / a.crb_acts];
+        const int4 qn = *reinterpret_cast<const int4*>(a.XqT + (size_t)(a.k_next + k) * a.Mp + m0 + mm0);
+        const int8_t* bn = reinterpret_cast<const int8_t*>(&qn);
 #pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      const int mm = mm0 + u;
-      if (mm < rows) {
-        float ea = eA[u], eb = eB[u];
+        for (int e = 0; e < 16; ++e) vn[e] = (mm0 + e < rows) ? dn * (float)bn[e] : 0.f;
         if (has_prev) {
-          float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+          const float dp = a.dX[(a.k_prev + k) / a.crb_acts];
+          const int4 qp = *reinterpret_cast<const int4*>(a.XqT + (size_t)(a.k_prev + k) * a.Mp + m0 + mm0);
+          const int8_t* bp = reinterpret_cast<const int8_t*>(&qp);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) vp[e] = (mm0 + e < rows) ? dp * (float)bp[e] : 0.f;
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 16; ++e) { xn[(mm0 + e) * KS + k] = vn[e]; xp[(mm0 + e) * KS + k] = vp[e]; }
+    }
+    __syncthreads();
+    constexpr int UN = 4;                                   // tokens in flight per thread and channel
+    for (int mm0 = 0; mm0 < rows; mm0 += UN) {
+      float eA[UN], gA[UN], eB[UN], gB[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const bool ok = mm0 + u < rows;
+        const size_t off = (size_t)(m0 + mm0 + u) * a.O;
+        eA[u] = (ok && okA) ? a.E[off + oA] : 0.f; gA[u] = (ok && okA) ? a.G[off + oA] * gs : 0.f;
+        eB[u] = (ok && okB) ? a.E[off + oB] : 0.f; gB[u] = (ok && okB) ? a.G[off + oB] * gs : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < UN; ++u) {
+        const int mm = mm0 + u;
+        if (mm < rows) {
+          float ea = eA[u], eb = eB[u];
+          if (has_prev) {
+            f32x2 sa = 0ull, sb = 0ull;
+#pragma unroll
+            for (int k = 0; k < KS; k += 4) {
+              const float4 xv = *reinterpret_cast<const float4*>(&xp[mm * KS + k]);
+              const f32x2 x01 = pack2(xv.x, xv.y), x23 = pack2(xv.z, xv.w);
+              sa = fma2(x01, dA[k / 2], sa); sa = fma2(x23, dA[k / 2 + 1], sa);
+              sb = fma2(x01, dB[k / 2], sb); sb = fma2(x23, dB[k / 2 + 1], sb);
+            }
+            float s0, s1; unpack2(sa, s0, s1); ea -= s0 + s1;
+            unpack2(sb, s0, s1); eb -= s0 + s1;
+            const size_t off = (size_t)(m0 + mm) * a.O;
+            if (okA) a.E[off + oA] = ea;
+            if (okB) a.E[off + oB] = eb;
+          }
+          const float geA = gA[u] * ea, geB = gB[u] * eb;
+          e2A = fmaf(geA, geA, e2A); e2B = fmaf(geB, geB, e2B);
+          const float wA = gA[u] * geA, wB = gB[u] * geB;
+          const f32x2 wA2 = pack2(wA, wA), wB2 = pack2(wB, wB);
 #pragma unroll
           for (int k = 0; k < KS; k += 4) {
-            const float4 xv = *reinterpret_cast<const float4*>(&xp[mm * KS + k]);
-            a0 = fmaf(xv.x, dA[k], a0); a1 = fmaf(xv.y, dA[k + 1], a1); a0 = fmaf(xv.z, dA[k + 2], a0); a1 = fmaf(xv.w, dA[k + 3], a1);
-            b0 = fmaf(xv.x, dB[k], b0); b1 = fmaf(xv.y, dB[k + 1], b1); b0 = fmaf(xv.z, dB[k + 2], b0); b1 = fmaf(xv.w, dB[k + 3], b1);
+            const float4 xv = *reinterpret_cast<const float4*>(&xn[mm * KS + k]);
+            const f32x2 x01 = pack2(xv.x, xv.y), x23 = pack2(xv.z, xv.w);
+            accA[k / 2] = fma2(wA2, x01, accA[k / 2]); accA[k / 2 + 1] = fma2(wA2, x23, accA[k / 2 + 1]);
+            accB[k / 2] = fma2(wB2, x01, accB[k / 2]); accB[k / 2 + 1] = fma2(wB2, x23, accB[k / 2 + 1]);
           }
-          ea -= a0 + a1; eb -= b0 + b1;
-          const size_t off = (size_t)(m0 + mm) * a.O;
-          if (okA) a.E[off + oA] = ea;
-          if (okB) a.E[off + oB] = eb;
-        }
-        const float geA = gA[u] * ea, geB = gB[u] * eb;
-        e2A = fmaf(geA, geA, e2A); e2B = fmaf(geB, geB, e2B);
-        const float wA = gA[u] * geA, wB = gB[u] * geB;
-#pragma unroll
-        for (int k = 0; k < KS; k += 4) {
-          const float4 xv = *reinterpret_cast<const float4*>(&xn[mm * KS + k]);
-          accA[k] = fmaf(wA, xv.x, accA[k]); accA[k + 1] = fmaf(wA, xv.y, accA[k + 1]);
-          accA[k + 2] = fmaf(wA, xv.z, accA[k + 2]); accA[k + 3] = fmaf(wA, xv.w, accA[k + 3]);
-          accB[k] = fmaf(wB, xv.x, accB[k]); accB[k + 1] = fmaf(wB, xv.y, accB[k + 1]);
-          accB[k + 2] = fmaf(wB, xv.z, accB[k + 2]); accB[k + 3] = fmaf(wB, xv.w, accB[k + 3]);
         }
       }
     }
   }
-  if (okA) {
-    float* up = a.Upart + ((size_t)blockIdx.y * a.O + oA) * a.ks;
 #pragma unroll
-    for (int k = 0; k < KS; ++k) if (k < a.ks) up[k] = accA[k];
-    a.E2part[(size_t)blockIdx.y * a.O + oA] = e2A;
-  }
-  if (okB) {
-    float* up = a.Upart + ((size_t)blockIdx.y * a.O + oB) * a.ks;
+  for (int half = 0; half < 2; ++half) {
+    const int o = half ? oB : oA;
+    if (o < a.O) {
+      float* up = a.Upart + ((size_t)blockIdx.y * a.O + o) * a.ks;
 #pragma unroll
-    for (int k = 0; k < KS; ++k) if (k < a.ks) up[k] = accB[k];
-    a.E2part[(size_t)blockIdx.y * a.O + oB] = e2B;
+      for (int k = 0; k < KS; k += 2) {
+        float u0, u1; unpack2(half ? accB[k / 2] : accA[k / 2], u0, u1);
+        if (k < a.ks) up[k] = u0;
+        if (k + 1 < a.ks) up[k + 1] = u1;
+      }
+      a.E2part[(size_t)blockIdx.y * a.O + o] = half ? e2B : e2A;
+    }
   }
 }
 
@@ -296,17 +317,30 @@ int p4v_pair_image(const int8_t* XqT, int Mp, int M, int k_first, int ks, int np
 }
 
 template <int KS> static int launch_update(const GramUpdateArgs& a, cudaStream_t st) {
-  dim3 grid(p4v_cdiv(a.O, 256), p4v_cdiv(a.M, GRAM_BM));
-  const size_t smem = (size_t)2 * GRAM_BM * KS * sizeof(float);
-  P4V_CUDA_OK(cudaFuncSetAttribute(gram_update_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  gram_update_kernel<KS><<<grid, 128, smem, st>>>(a); p4v_count_launch();
+  if (a.h_prev >= 0) {
+    const int n = a.O * KS;
+    gram_delta_kernel<<<p4v_cdiv(n, 256), 256, 0, st>>>(a.W, a.O, a.K, a.k_prev, a.ks, KS, a.dW, a.dW_prev, a.n_V, a.n_H, a.crb_rows,
+                                                        a.h_prev, a.w_lo, a.w_hi, a.D); p4v_count_launch();
+    P4V_CUDA_OK(cudaGetLastError());
+  }
+  dim3 grid(p4v_cdiv(a.O, 256), a.n_split);
+  gram_update_kernel<KS><<<grid, 128, 0, st>>>(a); p4v_count_launch();
   P4V_CUDA_OK(cudaGetLastError());
   return 0;
 }
 int p4v_gram_update(const GramUpdateArgs& a, cudaStream_t st) {
   P4V_REQUIRE(a.ks <= 64 && a.ks % 4 == 0, "gram: column block must be a multiple of 4 and <= 64 (got %d)", a.ks);
+  P4V_REQUIRE(a.n_split >= 1 && a.D != nullptr, "gram: bad update plan");
   if (a.ks <= 32) return launch_update<32>(a, st);
   return launch_update<64>(a, st);
+}
+int p4v_gram_update_splits(int O, int M) {      // token splits: one wave of two blocks per SM
+  int p4v_num_sms();
+  const int cb = p4v_cdiv(O, 256);
+  int s = (2 * p4v_num_sms()) / cb;
+  const int max_s = p4v_cdiv(M, GRAM_BM);
+  if (s > max_s) s = max_s;
+  return s < 1 ? 1 : s;
 }
 
 int p4v_gram_reduce(const float* Upart, const float* E2part, int n_mblk, int O, int ks, float* U, float* E2, cudaStream_t st) {

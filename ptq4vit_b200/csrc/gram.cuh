@@ -2,7 +2,7 @@
 #pragma once
 #include "common.cuh"
 
-#define GRAM_BM 64       // tokens per block of the update pass
+#define GRAM_BM 32       // tokens per shared-memory chunk of the update pass
 
 struct GramUpdateArgs {
   float* E; const float* G; const float* gscale;      // [M][O] residual (in/out), gradient, power-of-two scale
@@ -13,9 +13,11 @@ struct GramUpdateArgs {
   int n_V, n_H, crb_rows;
   int h_prev, k_prev, k_next, ks;                      // h_prev < 0: no update, only accumulate
   float w_lo, w_hi;
-  float* Upart; float* E2part;                         // [n_mblk][O][ks], [n_mblk][O]
+  float* Upart; float* E2part;                         // [n_split][O][ks], [n_split][O]
+  float* D; int n_split;                               // scratch [O][32 or 64] (weight deltas of the previous pick); token splits
 };
 int p4v_gram_update(const GramUpdateArgs& a, cudaStream_t st);
+int p4v_gram_update_splits(int O, int M);
 
 struct GramEvalArgs {
   const float* H; int ldH; int npairs;                 // [O][ldH] Gram of the integer activations (upper triangle, row-major pairs)

@@ -113,7 +113,7 @@ struct LinPlan {
   Step fwd;   // quant_forward: every segment is a fixed group
   // normal-equation W search (gram.cu)
   bool gram; int g_ks, g_Mp, g_npairs, g_tiles_p, g_ldH, g_nmblk; unsigned g_term_bytes;
-  size_t o_E, o_XqT, o_G2T, o_Z, o_H, o_Upart, o_E2part, o_U, o_E2, o_dprev, o_segsG;
+  size_t o_E, o_XqT, o_G2T, o_Z, o_H, o_Upart, o_E2part, o_U, o_E2, o_dprev, o_D, o_segsG;
   int g_osplit, g_opb;
   std::vector<float> factors;
   int max_groups;
@@ -203,7 +203,7 @@ int build_plan(const p4v_linear_desc* d, LinPlan& p, bool with_search) {
   for (size_t i = 0; i + 1 < cuts.size(); ++i) min_len = std::min(min_len, cuts[i + 1] - cuts[i]);
   if (d->operand == P4V_OPERAND_INT8) p.i8 = true;
   else if (d->operand == P4V_OPERAND_BF16) p.i8 = false;
-  else p.i8 = min_len >= 32;     // one kind::i8 K-step (32 elements) per slab or more: half the operand bytes of bf16
+  else p.i8 = min_len >= 64;     // short slabs are epilogue bound: integer-valued bf16 saves the int->float converts (measured)
   p.ew = p.i8 ? 1 : 2;
   p.segs.clear();
   int off = 0;
@@ -343,7 +343,7 @@ int build_plan(const p4v_linear_desc* d, LinPlan& p, bool with_search) {
       p.g_Mp = (int)align_up((size_t)p.M, 16) + 16;
       p.g_npairs = p.g_ks * (p.g_ks + 1) / 2;
       p.g_tiles_p = p4v_cdiv(p.g_npairs * d->n_H, GRAM_PT); p.g_ldH = p.g_tiles_p * GRAM_PT;   // all column blocks side by side
-      p.g_nmblk = p4v_cdiv(p.M, GRAM_BM);
+      p.g_nmblk = p4v_gram_update_splits(p.O, p.M);
       const size_t KBg = 2 * (size_t)term;
       p.o_E = take((size_t)p.M * p.O * 4);
       p.o_XqT = take((size_t)p.K * p.g_Mp);
@@ -355,6 +355,7 @@ int build_plan(const p4v_linear_desc* d, LinPlan& p, bool with_search) {
       p.o_U = take((size_t)p.O * p.g_ks * 4); p.o_E2 = take((size_t)p.O * 4);
       p.g_osplit = std::max(1, p4v_cdiv(p.crb_rows, 2)); p.g_opb = p4v_cdiv(p.crb_rows, p.g_osplit);
       p.o_dprev = take((size_t)d->n_V * 4);
+      p.o_D = take((size_t)p.O * 64 * 4);
       p.o_segsG = take(2 * sizeof(P4VSeg));
     }
   }
@@ -527,6 +528,7 @@ int gram_wsearch(const LinPlan& p, void* ws, const float* x, const float* W, con
     u.dW = at<float>(ws, p.o_dW); u.dW_prev = at<float>(ws, p.o_dprev); u.n_V = p.d.n_V; u.n_H = p.d.n_H; u.crb_rows = p.crb_rows;
     u.h_prev = h > h_begin ? h - 1 : -1; u.k_prev = (h - 1) * p.g_ks; u.k_next = h * p.g_ks; u.ks = p.g_ks;
     u.w_lo = w_lo; u.w_hi = w_hi; u.Upart = at<float>(ws, p.o_Upart); u.E2part = at<float>(ws, p.o_E2part);
+    u.D = at<float>(ws, p.o_D); u.n_split = p.g_nmblk;
     if ((rc = p4v_gram_update(u, st))) return rc;
     GramEvalArgs ev{};
     ev.H = at<float>(ws, p.o_H) + (size_t)(h - h_begin) * p.g_npairs; ev.ldH = p.g_ldH; ev.npairs = p.g_npairs;
