@@ -126,6 +126,11 @@ P4V_API long long p4v_launch_count(void);
  * executed, then clears the record. */
 P4V_API int p4v_profile_enable(int on);
 P4V_API int p4v_profile_collect(double* sweep_ms, long long* sweep_launches, double* executed_ops);
+/* Device self-test of the quantiser's division shortcut: evaluates round(v / delta) for n pseudo-random (v, delta)
+ * pairs (plus pairs placed on and next to rounding ties) both with IEEE division, as the reference does
+ * (quant_layers/linear.py:99-103 `(x / interval).round_()`), and with the reciprocal-based sequence the operand
+ * image kernels use; writes the number of disagreements (must be 0). */
+P4V_API int p4v_selftest_rint_div(unsigned long long n, unsigned long long seed, unsigned long long* mismatches, void* stream);
 
 #ifdef __cplusplus
 }

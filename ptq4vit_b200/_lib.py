@@ -44,7 +44,8 @@ _SIGNATURES = {
     "p4v_matmul_quant_forward_workspace_bytes": [C.POINTER(MatMulDesc), C.POINTER(C.c_size_t)],
     "p4v_matmul_quant_forward": [C.POINTER(MatMulDesc), _P, _P, _P, _P, _P, _P, C.c_size_t, _P, _P],
 }
-EXPORTS = sorted(list(_SIGNATURES) + ["p4v_last_error", "p4v_version", "p4v_launch_count", "p4v_profile_enable", "p4v_profile_collect"])
+EXPORTS = sorted(list(_SIGNATURES) + ["p4v_last_error", "p4v_version", "p4v_launch_count", "p4v_profile_enable", "p4v_profile_collect",
+                                     "p4v_selftest_rint_div"])
 
 _lib = None
 
@@ -66,6 +67,7 @@ def lib():
         l.p4v_version.restype = C.c_int
         l.p4v_launch_count.restype = C.c_longlong
         l.p4v_profile_enable.argtypes = [C.c_int]
+        l.p4v_selftest_rint_div.argtypes = [C.c_ulonglong, C.c_ulonglong, C.POINTER(C.c_ulonglong), C.c_void_p]
         l.p4v_profile_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.POINTER(C.c_double)]
         _lib = l
     return _lib

@@ -154,16 +154,23 @@ __global__ void __launch_bounds__(128) gram_update_kernel(const GramUpdateArgs a
       for (int e = 0; e < 16; ++e) { xn[(mm0 + e) * KS + k] = vn[e]; xp[(mm0 + e) * KS + k] = vp[e]; }
     }
     __syncthreads();
-    constexpr int UN = 4;                                   // tokens in flight per thread and channel
-    for (int mm0 = 0; mm0 < rows; mm0 += UN) {
-      float eA[UN], gA[UN], eB[UN], gB[UN];
+    constexpr int UN = 4;                                   // tokens per group; the NEXT group's e and g are in flight
+    float eAn[UN], gAn[UN], eBn[UN], gBn[UN];               // while the current group is multiplied (two warps per
+    auto fetch = [&](int mm0) {                            // scheduler: the loads must be hidden inside the thread)
 #pragma unroll
       for (int u = 0; u < UN; ++u) {
         const bool ok = mm0 + u < rows;
         const size_t off = (size_t)(m0 + mm0 + u) * a.O;
-        eA[u] = (ok && okA) ? a.E[off + oA] : 0.f; gA[u] = (ok && okA) ? a.G[off + oA] * gs : 0.f;
-        eB[u] = (ok && okB) ? a.E[off + oB] : 0.f; gB[u] = (ok && okB) ? a.G[off + oB] * gs : 0.f;
+        eAn[u] = (ok && okA) ? a.E[off + oA] : 0.f; gAn[u] = (ok && okA) ? a.G[off + oA] : 0.f;
+        eBn[u] = (ok && okB) ? a.E[off + oB] : 0.f; gBn[u] = (ok && okB) ? a.G[off + oB] : 0.f;
       }
+    };
+    fetch(0);
+    for (int mm0 = 0; mm0 < rows; mm0 += UN) {
+      float eA[UN], gA[UN], eB[UN], gB[UN];
+#pragma unroll
+      for (int u = 0; u < UN; ++u) { eA[u] = eAn[u]; gA[u] = gAn[u] * gs; eB[u] = eBn[u]; gB[u] = gBn[u] * gs; }
+      if (mm0 + UN < rows) fetch(mm0 + UN);
 #pragma unroll
       for (int u = 0; u < UN; ++u) {
         const int mm = mm0 + u;

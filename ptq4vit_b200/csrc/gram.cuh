@@ -2,7 +2,7 @@
 #pragma once
 #include "common.cuh"
 
-#define GRAM_BM 32       // tokens per shared-memory chunk of the update pass
+#define GRAM_BM 64       // tokens per shared-memory chunk of the update pass
 
 struct GramUpdateArgs {
   float* E; const float* G; const float* gscale;      // [M][O] residual (in/out), gradient, power-of-two scale

@@ -1,4 +1,5 @@
 #include "prep.cuh"
+#include "../../include/ptq4vit_b200.h"
 #include <math.h>
 
 void p4v_count_launch();
@@ -88,14 +89,28 @@ __global__ void make_gscale_kernel(const int* key, float* gscale) {
   gscale[0] = s;
 }
 
-// One thread = one (plane, problem, 16-byte chunk, padded row).  grid = (row blocks, P * chunks, planes): rows are
-// the fastest index so that the 16-byte stores of a warp are contiguous in the image.
+// rintf(__fdiv_rn(v, delta)) without the general-purpose division: rcp must be __frcp_rn(delta).
+// q1 = q0 + (v - delta*q0)*rcp differs from the correctly rounded quotient by at most one ulp, so rint(q1) equals
+// rint(v/delta) unless q1 lies within a few ulps of a half-integer; those (one in ~10^4) and non-finite values
+// take the exact division.  Only valid for 2^-100 < delta < 2^100 (checked once per plane by the caller).
+__device__ __forceinline__ float rint_div(float v, float delta, float rcp) {
+  const float q0 = v * rcp;
+  const float q1 = fmaf(fmaf(-delta, q0, v), rcp, q0);
+  const float n = rintf(q1);
+  const float aq = fabsf(q1);
+  const float dist = fabsf(fabsf(q1 - n) - 0.5f);
+  if (!(aq <= 3.0e38f) || dist <= aq * 4.8e-7f) return rintf(__fdiv_rn(v, delta));
+  return n;
+}
+
+// One thread = one (problem, 16-byte chunk, padded row) for a strided subset of the planes.  grid = (row blocks,
+// P * chunks, plane groups): rows are the fastest index so that the 16-byte stores of a warp are contiguous in the
+// image; the source values are loaded once and quantised for every plane (candidate step size) of the subset.
 template <bool kInt8>
 __global__ void quant_image_kernel(const QuantImageArgs a, int chunks_total) {
   const int rows_pad = a.tiles * P4V_TILE;
   const int row_p = blockIdx.x * blockDim.x + threadIdx.x;
   if (row_p >= rows_pad) return;
-  const int plane = blockIdx.z;
   const int p = blockIdx.y / chunks_total;
   int chunk = blockIdx.y % chunks_total;
   constexpr int epc = kInt8 ? 16 : 8;          // elements per 16-byte chunk
@@ -107,21 +122,19 @@ __global__ void quant_image_kernel(const QuantImageArgs a, int chunks_total) {
   }
   const P4VSeg sg = a.segs[s];
   const int tile = row_p / P4V_TILE, r = row_p % P4V_TILE;
-  uint8_t* dst = a.dst + (size_t)plane * a.plane_stride + ((size_t)p * a.tiles + tile) * a.tile_bytes + sg.dst_off +
-                 ((size_t)chunk * P4V_TILE + r) * 16;
-  uint32_t w[4] = {0u, 0u, 0u, 0u};
+  uint8_t* dst0 = a.dst + ((size_t)p * a.tiles + tile) * a.tile_bytes + sg.dst_off + ((size_t)chunk * P4V_TILE + r) * 16;
+  float vals[epc];
+  float delta0 = 1.f;
+  const bool plain = !(sg.sos_part || sg.split3);
   if (row_p < a.rows) {
-    float delta = 1.f;
-    const float split = sg.sos_part ? (a.factors ? a.factors[plane] : a.split[0]) : 0.f;
-    if (sg.sos_part || sg.split3) { /* step size handled below */ }
-    else if (sg.fixed_delta > 0.f) delta = sg.fixed_delta;
-    else {
-      const int rb = a.rows_per_block > 0 ? row_p / a.rows_per_block : (p % a.d_mod);
-      delta = a.delta[(size_t)rb * a.d_stride + sg.didx];
-      if (a.factors) delta = a.factors[plane] * delta;       // fl(f_c * delta0), as the reference's candidate table
+    if (plain) {
+      if (sg.fixed_delta > 0.f) delta0 = sg.fixed_delta;
+      else {
+        const int rb = a.rows_per_block > 0 ? row_p / a.rows_per_block : (p % a.d_mod);
+        delta0 = a.delta[(size_t)rb * a.d_stride + sg.didx];
+      }
     }
     const float* base = a.src + (size_t)p * a.prob_stride;
-    float vals[epc];
     if (!a.src_transposed && chunk * epc + epc <= sg.klen && ((a.ld | sg.k0) & 3) == 0) {
       const float4* src4 = reinterpret_cast<const float4*>(base + (size_t)row_p * a.ld + sg.k0 + chunk * epc);
 #pragma unroll
@@ -134,36 +147,51 @@ __global__ void quant_image_kernel(const QuantImageArgs a, int chunks_total) {
         vals[e] = kk < sg.klen ? (a.src_transposed ? base[(size_t)k * a.ld + row_p] : base[(size_t)row_p * a.ld + k]) : 0.f;
       }
     }
+    if (sg.square) {
+      const float ps = a.presc ? a.presc[0] : 1.f;
 #pragma unroll
-    for (int e = 0; e < epc; ++e) {
-      const int kk = chunk * epc + e;
-      float q = 0.f;
-      if (kk < sg.klen) {
-        float v = vals[e];
-        if (sg.square) { if (a.presc) v *= a.presc[0]; v = v * v; }
-        if (sg.split3) {
-          const float b1 = __bfloat162float(__float2bfloat16_rn(v));
-          const float b2 = __bfloat162float(__float2bfloat16_rn(v - b1));
-          q = sg.split3 == 1 ? b1 : (sg.split3 == 2 ? b2 : __bfloat162float(__float2bfloat16_rn((v - b1) - b2)));
-        } else if (sg.sos_part == 1) {
-          q = fminf(fmaxf(rintf(fminf(fmaxf(v, split), 1.f) * sg.qm1), 0.f), sg.qm1);
-        } else if (sg.sos_part == 2) {
-          q = fminf(fmaxf(rintf(__fdiv_rn(fminf(fmaxf(v, 0.f), split), __fdiv_rn(split, sg.qm1))), 0.f), sg.qm1);
-        } else {
-          q = fminf(fmaxf(rintf(__fdiv_rn(v, delta)), sg.lo), sg.hi);
-        }
-        if (!(q == q)) q = 0.f;   // NaN (0/0) cannot be represented in the integer operand
-      }
-      if constexpr (kInt8) {
-        const int qi = (int)q;
-        w[e >> 2] |= (uint32_t)(qi & 0xff) << ((e & 3) * 8);
-      } else {
-        const uint32_t hb = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(q));
-        w[e >> 1] |= hb << ((e & 1) * 16);
-      }
+      for (int e = 0; e < epc; ++e) { const float v = vals[e] * ps; vals[e] = v * v; }
     }
   }
-  *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+  for (int plane = blockIdx.z; plane < a.n_planes; plane += gridDim.z) {
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+    if (row_p < a.rows) {
+      const float split = sg.sos_part ? (a.factors ? a.factors[plane] : a.split[0]) : 0.f;
+      float delta = delta0;
+      if (plain && sg.fixed_delta <= 0.f && a.factors) delta = a.factors[plane] * delta0;   // fl(f_c * delta0), as the reference's candidate table
+      const float ad = fabsf(delta);
+      const bool fast = plain && ad > 7.9e-31f && ad < 1.2e30f;
+      const float rcp = fast ? __frcp_rn(delta) : 0.f;
+#pragma unroll
+      for (int e = 0; e < epc; ++e) {
+        const int kk = chunk * epc + e;
+        float q = 0.f;
+        if (kk < sg.klen) {
+          const float v = vals[e];
+          if (sg.split3) {
+            const float b1 = __bfloat162float(__float2bfloat16_rn(v));
+            const float b2 = __bfloat162float(__float2bfloat16_rn(v - b1));
+            q = sg.split3 == 1 ? b1 : (sg.split3 == 2 ? b2 : __bfloat162float(__float2bfloat16_rn((v - b1) - b2)));
+          } else if (sg.sos_part == 1) {
+            q = fminf(fmaxf(rintf(fminf(fmaxf(v, split), 1.f) * sg.qm1), 0.f), sg.qm1);
+          } else if (sg.sos_part == 2) {
+            q = fminf(fmaxf(rintf(__fdiv_rn(fminf(fmaxf(v, 0.f), split), __fdiv_rn(split, sg.qm1))), 0.f), sg.qm1);
+          } else {
+            q = fminf(fmaxf(fast ? rint_div(v, delta, rcp) : rintf(__fdiv_rn(v, delta)), sg.lo), sg.hi);
+          }
+          if (!(q == q)) q = 0.f;   // NaN (0/0) cannot be represented in the integer operand
+        }
+        if constexpr (kInt8) {
+          const int qi = (int)q;
+          w[e >> 2] |= (uint32_t)(qi & 0xff) << ((e & 3) * 8);
+        } else {
+          const uint32_t hb = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(q));
+          w[e >> 1] |= hb << ((e & 1) * 16);
+        }
+      }
+    }
+    *reinterpret_cast<uint4*>(dst0 + (size_t)plane * a.plane_stride) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
 }
 
 __device__ __forceinline__ void step_tables_body(const StepTablesArgs& a, int tid, int nthreads) {
@@ -345,12 +373,62 @@ int p4v_make_gscale(const int* key, float* gscale, cudaStream_t st) {
   return 0;
 }
 
+namespace {
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {       // splitmix64
+  z += 0x9E3779B97F4A7C15ull; z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__global__ void rint_div_selftest_kernel(unsigned long long n, unsigned long long seed, unsigned long long* mismatches) {
+  unsigned long long bad = 0;
+  for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long h = mix64(seed + i), h2 = mix64(h);
+    // delta: random mantissa, exponent 2^-24 .. 2^4; quotient target |q| < 300
+    const float delta = __uint_as_float(((unsigned)(103 + (h & 31)) << 23) | (unsigned)((h >> 8) & 0x7fffff));
+    float v;
+    const unsigned mode = (unsigned)(h2 & 3);
+    if (mode == 0) {            // free mantissa
+      v = __uint_as_float((unsigned)(h2 >> 32));
+      if (!(fabsf(v) < 3e38f)) v = 1.f;
+      v = fmodf(v, 300.f * delta);
+    } else {                    // on / next to a rounding tie: (k + 0.5) * delta, moved by -2..+2 ulps
+      const float k = (float)((int)((h2 >> 8) % 600) - 300) + 0.5f;
+      v = k * delta;
+      const int steps = (int)((h2 >> 40) % 5) - 2;
+      v = __uint_as_float(__float_as_uint(v) + steps);
+    }
+    const float want = rintf(__fdiv_rn(v, delta));
+    const float ad = fabsf(delta);
+    const float got = (ad > 7.9e-31f && ad < 1.2e30f) ? rint_div(v, delta, __frcp_rn(delta)) : want;
+    if (!(want == got) && !(want != want && got != got)) ++bad;
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+}  // namespace
+
+extern "C" int p4v_selftest_rint_div(unsigned long long n, unsigned long long seed, unsigned long long* mismatches, void* stream) {
+  P4V_REQUIRE(mismatches != nullptr, "selftest: null output");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long* d = nullptr;
+  P4V_CUDA_OK(cudaMalloc(&d, 8));
+  P4V_CUDA_OK(cudaMemsetAsync(d, 0, 8, st));
+  rint_div_selftest_kernel<<<148 * 8, 256, 0, st>>>(n, seed, d); p4v_count_launch();
+  P4V_CUDA_OK(cudaGetLastError());
+  P4V_CUDA_OK(cudaMemcpyAsync(mismatches, d, 8, cudaMemcpyDeviceToHost, st));
+  P4V_CUDA_OK(cudaStreamSynchronize(st));
+  P4V_CUDA_OK(cudaFree(d));
+  return 0;
+}
+
 int p4v_quant_image(const QuantImageArgs& a, cudaStream_t st) {
   const int chunks_total = (int)(a.tile_bytes / P4V_TILE / 16);     // every segment is padded to 32 B
   const int rows_pad = a.tiles * P4V_TILE;
   if (rows_pad == 0 || chunks_total == 0 || a.n_planes == 0 || a.P == 0) return 0;
   P4V_REQUIRE((long long)a.P * chunks_total <= 65535 && a.n_planes <= 65535, "quant_image: grid too large");
-  dim3 grid(p4v_cdiv(rows_pad, 128), a.P * chunks_total, a.n_planes);
+  const long long blocks_xy = (long long)p4v_cdiv(rows_pad, 128) * a.P * chunks_total;
+  long long zg = (4096 + blocks_xy - 1) / blocks_xy;        // enough blocks to fill the GPU, otherwise all planes per thread
+  if (zg > a.n_planes) zg = a.n_planes;
+  if (zg < 1) zg = 1;
+  dim3 grid(p4v_cdiv(rows_pad, 128), a.P * chunks_total, (unsigned)zg);
   if (a.is_int8) quant_image_kernel<true><<<grid, 128, 0, st>>>(a, chunks_total);
   else quant_image_kernel<false><<<grid, 128, 0, st>>>(a, chunks_total);
   p4v_count_launch();

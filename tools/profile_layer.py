@@ -43,3 +43,12 @@ if os.environ.get("P4V_PROFILE_LOG"):
     ms, n, ops = C.c_double(), C.c_longlong(), C.c_double()
     L.p4v_profile_collect(C.byref(ms), C.byref(n), C.byref(ops))
     print(f"sweep launches {n.value}, {ms.value:.3f} ms total, {ops.value / ms.value / 1e9:.1f} TFLOP/s executed")
+if os.environ.get("P4V_TORCH_PROF"):
+    from torch.profiler import profile, ProfilerActivity
+    with torch.no_grad(), profile(activities=[ProfilerActivity.CUDA]) as prof:
+        run(); torch.cuda.synchronize()
+    rows = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)
+    tot = sum(e.device_time_total for e in rows)
+    for e in rows[:18]:
+        print(f"{e.key[:70]:70s} {e.count:5d} {e.device_time_total:10.1f} us {100 * e.device_time_total / tot:5.1f}%  avg {e.device_time_total / e.count:8.1f}")
+    print(f"total device time {tot / 1e3:.2f} ms")
