@@ -320,16 +320,13 @@ def main():
         torch.cuda.empty_cache()
         d2h = 0
 
+        from ptq4vit_b200.utils.quant_calib import search_from_host
+        items = [(m, host[n]) for n, (m, _) in work.items()]
+
         def e2e_step():
+            # pinned host tensors -> (copy stream, one module ahead) -> search -> step sizes back to pinned host memory
             nonlocal d2h
-            d2h = 0
-            for n, (m, _) in work.items():
-                hb = host[n]
-                dev = {k: v.to(device, non_blocking=True) for k, v in hb.items()}
-                run_module(m, dev)
-                outs = [m.w_interval, m.a_interval] if "x" in hb else [torch.as_tensor(m.A_interval), m.B_interval]
-                for o in outs:
-                    d2h += torch.as_tensor(o).cpu().numel() * 4
+            _, d2h = search_from_host(items, device)
             gather_results(wrapped, owner, names, dist, device)
 
         e2e_step()

@@ -132,6 +132,64 @@ def result_width(modules):
 
 
 # ---------------------------------------------------------------- calibrators
+# ---------------------------------------------------------------- host-resident captures
+def search_from_host(items, device, out_host=None):
+    """Search a list of modules whose captured tensors live in (pinned) HOST memory, as the reference's calibrators
+    keep them (`.cpu()` in its hooks, `.cuda()` per module before the search; quant_calib.py:173-201, :317-356).
+
+    items: [(module, {"x"|"A","B", "y", "g": pinned cpu tensors})].  The host->device copies of module i+1 run on a
+    side stream while module i searches; the chosen step sizes are copied back asynchronously into pinned buffers and
+    one synchronisation ends the call.  Returns (h2d_bytes, d2h_bytes)."""
+    import os, time
+    dbg = os.environ.get("P4V_E2E_DEBUG")
+    t_stage = t_cal = t_out = 0.0
+    copy_stream = torch.cuda.Stream(device=device)
+    main = torch.cuda.current_stream(device)
+    h2d = d2h = 0
+
+    def stage(i):
+        with torch.cuda.stream(copy_stream):
+            dev = {k: v.to(device, non_blocking=True) for k, v in items[i][1].items()}
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return dev, ev
+
+    results = []
+    nxt = stage(0) if items else None
+    for i, (m, hb) in enumerate(items):
+        dev, ev = nxt
+        t0 = time.perf_counter()
+        nxt = stage(i + 1) if i + 1 < len(items) else None
+        t_stage += time.perf_counter() - t0
+        main.wait_event(ev)
+        for v in dev.values():
+            v.record_stream(main)
+        h2d += sum(v.numel() * v.element_size() for v in dev.values())
+        if "x" in dev:
+            m.raw_input, m.raw_out, m.raw_grad = dev["x"], dev["y"], dev["g"]
+        else:
+            m.raw_input, m.raw_out, m.raw_grad = [dev["A"], dev["B"]], dev["y"], dev["g"]
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            m.calibration_step2()
+        t_cal += time.perf_counter() - t0
+        t0 = time.perf_counter()
+        m.raw_input = m.raw_out = m.raw_grad = None
+        outs = [m.w_interval, m.a_interval] if "x" in dev else [torch.as_tensor(m.A_interval, device=device), m.B_interval]
+        for j, o in enumerate(outs):
+            o = torch.as_tensor(o, device=device).detach().reshape(-1).float()
+            buf = torch.empty(o.numel(), dtype=torch.float32, pin_memory=True) if out_host is None else out_host[i][j]
+            buf.copy_(o, non_blocking=True)
+            results.append(buf)
+            d2h += o.numel() * 4
+        t_out += time.perf_counter() - t0
+    t0 = time.perf_counter()
+    main.synchronize()
+    if dbg:
+        print(f"[search_from_host] host time: stage {t_stage:.3f}s calibrate {t_cal:.3f}s outputs {t_out:.3f}s final sync {time.perf_counter() - t0:.3f}s", flush=True)
+    return h2d, d2h
+
+
 class QuantCalibrator():
     """reference: utils/quant_calib.py:9-171"""
 
