@@ -24,6 +24,11 @@
 
 namespace {
 
+#ifdef P4V_DEBUG_MODES   // debug build only (-DP4V_DEBUG_MODES): runtime-selectable partial execution, see SweepParams::debug_mode
+#define DBG_MODE(P) ((P).debug_mode)
+#else
+#define DBG_MODE(P) 0
+#endif
 #ifdef P4V_TRACE   // debug build only: clock64 timeline of CTA 0 (tools/trace_sweep.py)
 #define TRACE(role, ev, col) do { if (P.trace && blockIdx.x == 0 && (ev) < 512 && (threadIdx.x & 31) == 0) P.trace[((role) * 512 + (ev)) * 4 + (col)] = clock64(); } while (0)
 #else
@@ -519,7 +524,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
       uint32_t stage = 0, phase = 0, rbuf = 0, rphase = 0, cphase = 0;
       [[maybe_unused]] int tev = 0;
       const uint32_t full0 = smem_u32(&S.full[0]), empty0 = smem_u32(&S.empty[0]);
-      while (!(P.debug_mode & 1) && next_frag(P, sched, f)) {
+      while (!(DBG_MODE(P) & 1) && next_frag(P, sched, f)) {
         const size_t rt = (size_t)(f.p * P.tiles_m + f.tm), ct = (size_t)(f.p * P.tiles_n + f.tn);
         const uint8_t* r_cur = P.R_cur + rt * P.R_tile_bytes;
         const uint8_t* c_cur = P.C_cur + ct * P.C_tile_bytes;
@@ -609,7 +614,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
           return;
         }
         TRACE(1, tev, 0);
-        if (!(P.debug_mode & 1)) mbar_wait_addr(full0 + stage * 8, phase);
+        if (!(DBG_MODE(P) & 1)) mbar_wait_addr(full0 + stage * 8, phase);
         TRACE(1, tev, 1);
         tc_fence_after();
         uint32_t a16 = (flags & P4V_JOB_RRES) ? ra16 : ringR16 + stage * sR16;
@@ -617,7 +622,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
         for (uint32_t sub = 0; sub < nsub; ++sub) {
           if (flags & P4V_JOB_FIRST) mbar_wait_addr(acce0 + slot * 8, slot_phase ^ 1);
           TRACE(1, tev, 2);
-          if (P.debug_mode & 1) {
+          if (DBG_MODE(P) & 1) {
             if ((flags & P4V_JOB_LAST) && elect_one()) tc_commit_addr(accf0 + slot * 8);
           } else if (elect_one()) {
             const uint64_t da = dconst | (uint64_t)a16, db = dconst | (uint64_t)b16;
@@ -636,11 +641,11 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
         if (++stage == nst) { stage = 0; phase ^= 1; }
       };
       while (next_frag(P, sched, f)) {
-        if (cresB) { if (!(P.debug_mode & 1)) mbar_wait(&S.cres_full, cphase); cphase ^= 1; }
+        if (cresB) { if (!(DBG_MODE(P) & 1)) mbar_wait(&S.cres_full, cphase); cphase ^= 1; }
         for (int j = 0; j < P.n_fixed_jobs; ++j) run(S.jobs[j], 0u);
         uint32_t res16 = 0;
         if (resB) {
-          if (!(P.debug_mode & 1)) mbar_wait(&S.res_full[rbuf], rphase);
+          if (!(DBG_MODE(P) & 1)) mbar_wait(&S.res_full[rbuf], rphase);
           res16 = ((resR + rbuf * resB) & 0x3FFFF) >> 4;
         }
         if (P.n_cand_jobs == 1) {              // loop-invariant job: keep its fields in registers
@@ -655,10 +660,10 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
             }
         }
         if (resB) {
-          if (!(P.debug_mode & 1) && elect_one()) tc_commit(&S.res_empty[rbuf]);   // resident buffer free once every MMA reading it has retired
+          if (!(DBG_MODE(P) & 1) && elect_one()) tc_commit(&S.res_empty[rbuf]);   // resident buffer free once every MMA reading it has retired
           if (++rbuf == P.resident_bufs) { rbuf = 0; rphase ^= 1; }
         }
-        if (cresB && !(P.debug_mode & 1) && elect_one()) tc_commit(&S.cres_empty);
+        if (cresB && !(DBG_MODE(P) & 1) && elect_one()) tc_commit(&S.cres_empty);
       }
     }
   }
@@ -674,7 +679,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
     const uint32_t tstore = tmem + lane_addr + hf * 64;                 // parked residual target (!kSingle)
     const float gs = (P.out && !P.out_residual) ? 1.f : *P.gscale;
     AccRing ring{0u, 0u, kSlots};
-    const bool dbg2 = P.debug_mode & 2;
+    const bool dbg2 = DBG_MODE(P) & 2;
     [[maybe_unused]] int tev = 0;
     if constexpr (!kSingle) {
     // ---------------- several accumulators per candidate (or output mode) ----------------
@@ -752,18 +757,18 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
       tmem_st32(tstore, r);
       tmem_st32(tstore + 32, r + 32);
       tmem_wait_st();
+      if (f.c1 > f.c0) accm_begin(S, ring, tbase, a0);       // later candidates: prefetched by the previous candidate's last step
       for (int c = f.c0; c < f.c1; ++c) {
         const float4 ca = *reinterpret_cast<const float4*>(&S.candA[c][hf * 4]);
         tmem_ld32f(tstore, r);
         tmem_ld32f(tstore + 32, r + 32);
         tmem_wait_ld();
-        accm_begin(S, ring, tbase, a0);
         for (int gi = 0; gi < P.n_cand_groups; ++gi) {
           const float4 cb = *reinterpret_cast<const float4*>(&S.candB[gi][hf * 4]);
           const bool noA = (P.cand_noA_mask >> gi) & 1ull;
           const float4 sc = noA ? cb : make_float4(ca.x * cb.x, ca.y * cb.y, ca.z * cb.z, ca.w * cb.w);
           if (ew == 0) TRACE(2, tev, 0);
-          if (gi == P.n_cand_groups - 1) accm_step<kInt8, true, kPacked>(S, ring, tbase, lane, a0, a1, r, gp, sc, p, false, dbg2);
+          if (gi == P.n_cand_groups - 1) accm_step<kInt8, true, kPacked>(S, ring, tbase, lane, a0, a1, r, gp, sc, p, c + 1 < f.c1, dbg2);
           else accm_step<kInt8, false, kPacked>(S, ring, tbase, lane, a0, a1, r, gp, sc, p, true, dbg2);
           if (ew == 0) { TRACE(2, tev, 1); ++tev; }
         }
