@@ -76,7 +76,6 @@ struct SweepParams {
   // shared-memory plan, filled by the launcher
   unsigned int stage_r_bytes, stage_c_bytes, n_stages, resident_bytes, resident_bufs, cres_bytes;
   long long* trace;         // debug: clock64 timeline of CTA 0 ([3 roles][512 events][4]) or null
-  int mma_warps;            // 1 or 2 MMA issuer warps (launcher; env P4V_MMA_WARPS)
   int debug_mode;           // debug (env P4V_SWEEP_DEBUG): 1 = no operand traffic / no MMA (epilogue + handshakes only), 2 = epilogue does no math
 };
 

@@ -498,8 +498,8 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
   if (threadIdx.x == 0) {
     for (uint32_t i = 0; i < nst; ++i) { mbar_init(&S.full[i], 1); mbar_init(&S.empty[i], 1); }
     for (int i = 0; i < 4; ++i) { mbar_init(&S.acc_full[i], 1); mbar_init(&S.acc_empty[i], kEpiWarps); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&S.res_full[i], 1); mbar_init(&S.res_empty[i], P.mma_warps); }
-    mbar_init(&S.cres_full, 1); mbar_init(&S.cres_empty, P.mma_warps);
+    for (int i = 0; i < 2; ++i) { mbar_init(&S.res_full[i], 1); mbar_init(&S.res_empty[i], 1); }
+    mbar_init(&S.cres_full, 1); mbar_init(&S.cres_empty, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -585,11 +585,8 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
         }
       }
     }
-  } else if (warp == 1 || (warp == 2 && P.mma_warps == 2)) {
-    // ======================= MMA issuer(s) (whole warp runs the loop, one elected lane issues) =======================
-    // With two issuer warps the jobs (= stages; multi-job accumulation chains stay together) alternate between them:
-    // the owner waits for the stage, issues, and hands the stage and the accumulators on; the other warp only
-    // advances its ring counters.  Each warp's loop is latency bound, two of them double the issue rate.
+  } else if (warp == 1) {
+    // ======================= MMA issuer (whole warp runs the loop, one elected lane issues) =======================
     {
       uint32_t stage = 0, phase = 0, slot = 0, slot_phase = 0, rbuf = 0, rphase = 0;
       const uint32_t full0 = smem_u32(&S.full[0]), empty0 = smem_u32(&S.empty[0]);
@@ -602,17 +599,8 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
       const uint32_t resC16 = (resC & 0x3FFFF) >> 4;
       // one job = one stage: wait for its bytes, then per sub-accumulator (slot if FIRST, K-steps, publish if LAST);
       // the stage goes back to the producer with the last sub-accumulator
-      const uint32_t me = warp - 1, two = P.mma_warps == 2;
-      uint32_t chain = 0;
       auto run = [&](const P4VJob jb, const uint32_t ra16) {
         const uint32_t flags = jb.flags, kb = jb.kb, nsub = p4v_job_nsub(jb);
-        const bool mine = !two || (chain & 1u) == me;
-        if (flags & P4V_JOB_LAST) ++chain;
-        if (!mine) {                                    // the other issuer's job: keep the ring counters in step
-          if (flags & P4V_JOB_LAST) for (uint32_t sub = 0; sub < nsub; ++sub) { if (++slot == kSlots) { slot = 0; slot_phase ^= 1; } }
-          if (++stage == nst) { stage = 0; phase ^= 1; }
-          return;
-        }
         TRACE(1, tev, 0);
         if (!(DBG_MODE(P) & 1)) mbar_wait_addr(full0 + stage * 8, phase);
         TRACE(1, tev, 1);
@@ -951,8 +939,6 @@ int p4v_launch_sweep_tc(const SweepParams& p_in, const P4VJob* host_jobs, int nu
   } while (0)
 #define P4V_LAUNCH2(I8, SG) do { if (packed) P4V_LAUNCH(I8, SG, true); else P4V_LAUNCH(I8, SG, false); } while (0)
   p.debug_mode = g_sweep_debug;
-  static const int mma_warps = [] { const char* e = getenv("P4V_MMA_WARPS"); return (e && atoi(e) == 2) ? 2 : 1; }();   // 2 = experimental second issuer warp
-  p.mma_warps = mma_warps;
   static const bool packed = [] { const char* e = getenv("P4V_PACKED"); return e ? atoi(e) != 0 : true; }();
   if (p.is_int8) { if (single) P4V_LAUNCH2(true, true); else P4V_LAUNCH2(true, false); }
   else           { if (single) P4V_LAUNCH2(false, true); else P4V_LAUNCH2(false, false); }
