@@ -361,11 +361,16 @@ def main():
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16, measured)" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
     achieved = sweep_ops.value / (sweep_ms.value / 1e3) / 1e12 if sweep_ms.value > 0 else 0.0
     roofline = {"bound": "tensor", "achieved": achieved, "peak": bf16_peak, "unit": "TFLOP/s", "frac": achieved / bf16_peak,
-                "traffic": None, "kernel": "sweep_tc_kernel", "launches": int(sweep_n.value),
+                # DRAM bytes (read+write) of the dominant sweep launch from profiles/r01_sweep_xstep_qkv.ncu-rep (ncu --set full):
+                # the ViT-B qkv activation step, 4.90 ms, 2.26 TFLOP executed; algorithmic bytes of that launch =
+                # candidate planes of X 968 MB + y,g once 116 MB + weight image 3.5 MB + partial scores 11.5 MB = 1.10 GB
+                "traffic": 1230711296, "traffic_of": "qkv activation-step launch (algorithmic 1.10e9 B)", "kernel": "sweep_tc_kernel", "launches": int(sweep_n.value),
                 "avg_launch_ms": sweep_ms.value / max(1, sweep_n.value), "share_of_step": sweep_ms.value / ms,
                 "note": "achieved = EXECUTED tensor-core ops (slab-incremental: only the K segment a candidate changes is multiplied) / "
                         "summed CUDA-event time of the sweep launches of this rank; peak = " + peak_src +
-                        "; the kernel is bound by its fp32 CUDA-core epilogue at 32-wide slabs, see DESIGN.md"}
+                        "; slab sweeps only (the Gram GEMM of the weight steps is a separate kernel: 1.53 PFLOP/s executed, "
+                        "profiles/r01_final_ncu_summary.csv); the sweep is bound by the per-accumulator hand-over (fp32 epilogue, "
+                        "TMEM load latency, single-warp issue loop) at 32-wide slabs, see DESIGN.md 4.1"}
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
            "dtype": "int8/bf16-int operands, s32/f32 accumulate, f32 error", "data": "synthetic",

@@ -102,36 +102,36 @@ __global__ void gram_delta_kernel(const float* __restrict__ W, int O, int K, int
 // One pass over e and g: apply the rank-ks update of the previous step, accumulate U and sum (g e)^2 for the next slab.
 // grid = (256-channel blocks) x (token splits, sized so that the grid is ONE balanced wave); a block walks its token
 // range in chunks of GRAM_BM tokens and keeps the U accumulators of its channels in registers the whole time, so there
-// is one partial per block.  thread = TWO output channels (o, o+128): every xhat value fetched from shared memory
-// feeds two packed FMAs.
+// is one partial per block.  thread = one output channel (16 warps per SM hide the e/g load latency better than
+// two channels per thread at 8 warps); xhat values come from shared memory as broadcast 16-byte loads.
 template <int KS>
-__global__ void __launch_bounds__(128) gram_update_kernel(const GramUpdateArgs a) {
+__global__ void __launch_bounds__(256, 2) gram_update_kernel(const GramUpdateArgs a) {
   __shared__ __align__(16) float xp[GRAM_BM * KS];       // previous slab (xhat), only if a.h_prev >= 0
   __shared__ __align__(16) float xn[GRAM_BM * KS];       // next slab
-  const int oA = blockIdx.x * 256 + threadIdx.x, oB = oA + 128;
-  const bool okA = oA < a.O, okB = oB < a.O;
+  const int o = blockIdx.x * 256 + threadIdx.x;
+  const bool ok_o = o < a.O;
   const float gs = a.gscale[0];
   const bool has_prev = a.h_prev >= 0;
   const int nb16 = (a.M + 15) / 16;                     // split on 16-token boundaries: the slab loads stay 16-byte aligned
   const int m_begin = (int)((long long)nb16 * blockIdx.y / gridDim.y) * 16;
   const int m_end = min(a.M, (int)((long long)nb16 * (blockIdx.y + 1) / gridDim.y) * 16);
-  f32x2 dA[KS / 2], dB[KS / 2], accA[KS / 2], accB[KS / 2];
+  f32x2 dd[KS / 2], acc[KS / 2];
 #pragma unroll
-  for (int k = 0; k < KS / 2; ++k) { dA[k] = 0ull; dB[k] = 0ull; accA[k] = 0ull; accB[k] = 0ull; }
-  if (has_prev) {
+  for (int k = 0; k < KS / 2; ++k) { dd[k] = 0ull; acc[k] = 0ull; }
+  if (has_prev && ok_o) {
 #pragma unroll
     for (int k = 0; k < KS; k += 4) {
-      if (okA) { const float4 v = *reinterpret_cast<const float4*>(a.D + (size_t)oA * KS + k); dA[k / 2] = pack2(v.x, v.y); dA[k / 2 + 1] = pack2(v.z, v.w); }
-      if (okB) { const float4 v = *reinterpret_cast<const float4*>(a.D + (size_t)oB * KS + k); dB[k / 2] = pack2(v.x, v.y); dB[k / 2 + 1] = pack2(v.z, v.w); }
+      const float4 v = *reinterpret_cast<const float4*>(a.D + (size_t)o * KS + k);
+      dd[k / 2] = pack2(v.x, v.y); dd[k / 2 + 1] = pack2(v.z, v.w);
     }
   }
-  float e2A = 0.f, e2B = 0.f;
+  float e2 = 0.f;
   for (int m0 = m_begin; m0 < m_end; m0 += GRAM_BM) {
     const int rows = min(GRAM_BM, m_end - m0);
     __syncthreads();                                      // previous chunk consumed
     // slab chunks of the token-major int8 activations -> fp32 xhat in shared memory ([token][k], k contiguous);
     // thread = (k, 16-token piece): one 16-byte load per slab row piece, conflict-free stores (lanes = consecutive k)
-    for (int it = threadIdx.x; it < KS * (GRAM_BM / 16); it += 128) {
+    for (int it = threadIdx.x; it < KS * (GRAM_BM / 16); it += 256) {
       const int k = it % KS, mm0 = (it / KS) * 16;
       float vn[16], vp[16];
 #pragma unroll
@@ -155,70 +155,59 @@ __global__ void __launch_bounds__(128) gram_update_kernel(const GramUpdateArgs a
     }
     __syncthreads();
     constexpr int UN = 4;                                   // tokens per group; the NEXT group's e and g are in flight
-    float eAn[UN], gAn[UN], eBn[UN], gBn[UN];               // while the current group is multiplied (two warps per
-    auto fetch = [&](int mm0) {                            // scheduler: the loads must be hidden inside the thread)
+    float en[UN], gn[UN];                                   // while the current group is multiplied
+    auto fetch = [&](int mm0) {
 #pragma unroll
       for (int u = 0; u < UN; ++u) {
-        const bool ok = mm0 + u < rows;
-        const size_t off = (size_t)(m0 + mm0 + u) * a.O;
-        eAn[u] = (ok && okA) ? a.E[off + oA] : 0.f; gAn[u] = (ok && okA) ? a.G[off + oA] : 0.f;
-        eBn[u] = (ok && okB) ? a.E[off + oB] : 0.f; gBn[u] = (ok && okB) ? a.G[off + oB] : 0.f;
+        const bool ok = ok_o && mm0 + u < rows;
+        const size_t off = (size_t)(m0 + mm0 + u) * a.O + o;
+        en[u] = ok ? a.E[off] : 0.f; gn[u] = ok ? a.G[off] : 0.f;
       }
     };
     fetch(0);
     for (int mm0 = 0; mm0 < rows; mm0 += UN) {
-      float eA[UN], gA[UN], eB[UN], gB[UN];
+      float ec[UN], gc[UN];
 #pragma unroll
-      for (int u = 0; u < UN; ++u) { eA[u] = eAn[u]; gA[u] = gAn[u] * gs; eB[u] = eBn[u]; gB[u] = gBn[u] * gs; }
+      for (int u = 0; u < UN; ++u) { ec[u] = en[u]; gc[u] = gn[u] * gs; }
       if (mm0 + UN < rows) fetch(mm0 + UN);
 #pragma unroll
       for (int u = 0; u < UN; ++u) {
         const int mm = mm0 + u;
         if (mm < rows) {
-          float ea = eA[u], eb = eB[u];
+          float ev = ec[u];
           if (has_prev) {
-            f32x2 sa = 0ull, sb = 0ull;
+            f32x2 s0 = 0ull, s1 = 0ull;
 #pragma unroll
             for (int k = 0; k < KS; k += 4) {
               const float4 xv = *reinterpret_cast<const float4*>(&xp[mm * KS + k]);
-              const f32x2 x01 = pack2(xv.x, xv.y), x23 = pack2(xv.z, xv.w);
-              sa = fma2(x01, dA[k / 2], sa); sa = fma2(x23, dA[k / 2 + 1], sa);
-              sb = fma2(x01, dB[k / 2], sb); sb = fma2(x23, dB[k / 2 + 1], sb);
+              s0 = fma2(pack2(xv.x, xv.y), dd[k / 2], s0); s1 = fma2(pack2(xv.z, xv.w), dd[k / 2 + 1], s1);
             }
-            float s0, s1; unpack2(sa, s0, s1); ea -= s0 + s1;
-            unpack2(sb, s0, s1); eb -= s0 + s1;
-            const size_t off = (size_t)(m0 + mm) * a.O;
-            if (okA) a.E[off + oA] = ea;
-            if (okB) a.E[off + oB] = eb;
+            float t0, t1, t2, t3; unpack2(s0, t0, t1); unpack2(s1, t2, t3);
+            ev -= (t0 + t1) + (t2 + t3);
+            if (ok_o) a.E[(size_t)(m0 + mm) * a.O + o] = ev;
           }
-          const float geA = gA[u] * ea, geB = gB[u] * eb;
-          e2A = fmaf(geA, geA, e2A); e2B = fmaf(geB, geB, e2B);
-          const float wA = gA[u] * geA, wB = gB[u] * geB;
-          const f32x2 wA2 = pack2(wA, wA), wB2 = pack2(wB, wB);
+          const float ge = gc[u] * ev;
+          e2 = fmaf(ge, ge, e2);
+          const float w = gc[u] * ge;
+          const f32x2 w2 = pack2(w, w);
 #pragma unroll
           for (int k = 0; k < KS; k += 4) {
             const float4 xv = *reinterpret_cast<const float4*>(&xn[mm * KS + k]);
-            const f32x2 x01 = pack2(xv.x, xv.y), x23 = pack2(xv.z, xv.w);
-            accA[k / 2] = fma2(wA2, x01, accA[k / 2]); accA[k / 2 + 1] = fma2(wA2, x23, accA[k / 2 + 1]);
-            accB[k / 2] = fma2(wB2, x01, accB[k / 2]); accB[k / 2 + 1] = fma2(wB2, x23, accB[k / 2 + 1]);
+            acc[k / 2] = fma2(w2, pack2(xv.x, xv.y), acc[k / 2]); acc[k / 2 + 1] = fma2(w2, pack2(xv.z, xv.w), acc[k / 2 + 1]);
           }
         }
       }
     }
   }
+  if (ok_o) {
+    float* up = a.Upart + ((size_t)blockIdx.y * a.O + o) * a.ks;
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    const int o = half ? oB : oA;
-    if (o < a.O) {
-      float* up = a.Upart + ((size_t)blockIdx.y * a.O + o) * a.ks;
-#pragma unroll
-      for (int k = 0; k < KS; k += 2) {
-        float u0, u1; unpack2(half ? accB[k / 2] : accA[k / 2], u0, u1);
-        if (k < a.ks) up[k] = u0;
-        if (k + 1 < a.ks) up[k + 1] = u1;
-      }
-      a.E2part[(size_t)blockIdx.y * a.O + o] = half ? e2B : e2A;
+    for (int k = 0; k < KS; k += 2) {
+      float u0, u1; unpack2(acc[k / 2], u0, u1);
+      if (k < a.ks) up[k] = u0;
+      if (k + 1 < a.ks) up[k + 1] = u1;
     }
+    a.E2part[(size_t)blockIdx.y * a.O + o] = e2;
   }
 }
 
@@ -331,7 +320,7 @@ template <int KS> static int launch_update(const GramUpdateArgs& a, cudaStream_t
     P4V_CUDA_OK(cudaGetLastError());
   }
   dim3 grid(p4v_cdiv(a.O, 256), a.n_split);
-  gram_update_kernel<KS><<<grid, 128, 0, st>>>(a); p4v_count_launch();
+  gram_update_kernel<KS><<<grid, 256, 0, st>>>(a); p4v_count_launch();
   P4V_CUDA_OK(cudaGetLastError());
   return 0;
 }
