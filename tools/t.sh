@@ -1,2 +1,4 @@
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-P4V_TORCH_PROF=1 timeout 100 python tools/profile_layer.py qkv 1 2>&1 | grep -E "rounds=|gram_update|gram_eval|total device"
+timeout 800 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; tail -2 gpurun_out/bench_final.err
+python -c "
+import json; d=json.load(open('gpurun_out/bench_final.json')); print({k:d[k] for k in ('value','ms_per_step','gpu_launches','clocks')}, d['roofline']['frac'], d['roofline']['share_of_step'], d['e2e'], d['cpu_baseline']['value'])"
+timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; tail -2 gpurun_out/bench_ref.err; cut -c1-400 gpurun_out/bench_ref.json
