@@ -8,14 +8,18 @@
 // One persistent CTA per SM.  Work = (output tile 128x128) x (candidates).  Whole tiles are dealt
 // round-robin in waves of gridDim.x (CTAs that run together share operand tiles in L2); the last partial
 // wave is split at candidate granularity so that every SM finishes together.  Per tile fragment:
-//   1. the 256 epilogue threads load r = y - bias and g = grad * 2^k for their (row, 64 columns) into
-//      REGISTERS -- they stay there for all candidates;
+//   1. the 256 epilogue threads load r = y - bias and g = grad * 2^k for their (row, 64 columns): r into
+//      registers; g into registers (single-segment steps) or into this thread's shared-memory row
+//      (multi-segment steps, where it is needed once per candidate);
 //   2. "fixed" segments (everything the candidate does not change) are multiplied on the tensor cores and
 //      subtracted: r -= scale * acc;
-//   3. per candidate only the segment(s) touched by the candidate step size are multiplied (TMA bulk copy
+//   3. per candidate only the segment(s) touched by the candidate step size are multiplied (bulk copy
 //      -> smem ring -> tcgen05.mma -> TMEM); the epilogue forms (g * (r - scale_c * acc))^2 straight from
-//      TMEM, reduces it over the 32 rows of a warp with shuffles and writes one partial per 16 columns.
-// Roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 4..11 = epilogue
+//      TMEM and writes one partial per (row quarter, 16 columns): single-segment steps sum the rows through
+//      shared memory in batches of candidates, multi-segment steps with a shuffle butterfly per candidate.
+// A job = one ring stage = up to 128 bytes of K of both operands, possibly several adjacent K slabs with an
+// accumulator each (P4VJob::nsub); operands that do not change between candidates stay resident in shared memory.
+// Roles: warp 0 = bulk-copy producer, warp 1 = MMA issuer (+TMEM alloc), warps 4..11 = epilogue
 // (setmaxnreg moves the register budget of warpgroup 0 to the epilogue warpgroups).
 #include "common.cuh"
 #include <algorithm>
@@ -132,14 +136,8 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(void* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// K-major, no swizzle: core matrix = 8 rows x 16 B; LBO = stride between the two
-// 16-byte chunks of one K-step, SBO = stride between 8-row groups.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-  constexpr uint64_t lbo = (P4V_TILE * 16) >> 4;   // 2048 B
-  constexpr uint64_t sbo = 128 >> 4;               // 128 B
-  return (uint64_t)((saddr & 0x3FFFF) >> 4) | (lbo << 16) | (sbo << 32) | (1ull << 46);
-}
-// descriptor with the constant fields only; the 14-bit start-address field (bits 0..13, units of 16 B) is added per use
+// K-major, no swizzle: core matrix = 8 rows x 16 B; LBO = stride between the 16-byte chunks of one K-step (2048 B),
+// SBO = stride between 8-row groups (128 B).  Descriptor with the constant fields only; the 14-bit start-address field (bits 0..13, units of 16 B) is added per use
 __device__ __forceinline__ uint64_t desc_hi_const() {
   constexpr uint64_t lbo = (P4V_TILE * 16) >> 4, sbo = 128 >> 4;
   return (lbo << 16) | (sbo << 32) | (1ull << 46);
@@ -159,17 +157,6 @@ __device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t da, uint64_t db, 
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(d_tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
   }
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
@@ -285,37 +272,7 @@ __device__ __forceinline__ void consume16(const uint32_t (&a)[16], float (&r)[64
   }
 }
 
-// Reduce 16 per-lane values (4 candidates x 4 column groups) over the 32 lanes (= rows) of the warp.
-// Afterwards lane L holds the total of value 8*b4 + 4*b3 + 2*b2 + b1 (bk = bit k of L).  Fixed order.
-__device__ __forceinline__ float reduce16_over_rows(float (&v)[16], int lane) {
-  const unsigned full = 0xffffffffu;
-  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
-  float w8[8], w4[4], w2[2];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) { const float send = b4 ? v[i] : v[8 + i]; const float keep = b4 ? v[8 + i] : v[i]; w8[i] = keep + __shfl_xor_sync(full, send, 16); }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) { const float send = b3 ? w8[i] : w8[4 + i]; const float keep = b3 ? w8[4 + i] : w8[i]; w4[i] = keep + __shfl_xor_sync(full, send, 8); }
-#pragma unroll
-  for (int i = 0; i < 2; ++i) { const float send = b2 ? w4[i] : w4[2 + i]; const float keep = b2 ? w4[2 + i] : w4[i]; w2[i] = keep + __shfl_xor_sync(full, send, 4); }
-  const float send = b1 ? w2[0] : w2[1]; float k = (b1 ? w2[1] : w2[0]) + __shfl_xor_sync(full, send, 2);
-  k += __shfl_xor_sync(full, k, 1);
-  return k;
-}
-// Same for 8 values (2 candidates x 4 groups): lane L holds value 4*b4 + 2*b3 + b2.
-__device__ __forceinline__ float reduce8_over_rows(float (&v)[8], int lane) {
-  const unsigned full = 0xffffffffu;
-  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
-  float w4[4], w2[2];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) { const float send = b4 ? v[i] : v[4 + i]; const float keep = b4 ? v[4 + i] : v[i]; w4[i] = keep + __shfl_xor_sync(full, send, 16); }
-#pragma unroll
-  for (int i = 0; i < 2; ++i) { const float send = b3 ? w4[i] : w4[2 + i]; const float keep = b3 ? w4[2 + i] : w4[i]; w2[i] = keep + __shfl_xor_sync(full, send, 8); }
-  const float send = b2 ? w2[0] : w2[1]; float k = (b2 ? w2[1] : w2[0]) + __shfl_xor_sync(full, send, 4);
-  k += __shfl_xor_sync(full, k, 2);
-  k += __shfl_xor_sync(full, k, 1);
-  return k;
-}
-// Same for 4 values: lane 8*k holds value k.
+// Reduce 4 per-lane values over the 32 lanes (= rows) of the warp, fixed order: lane 8*k ends up with the total of value k.
 __device__ __forceinline__ float reduce4_over_rows(float v0, float v1, float v2, float v3, int lane) {
   const unsigned full = 0xffffffffu;
   const bool hi16 = lane & 16;
@@ -836,8 +793,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
         }
         continue;
       }
-      float* part_base = P.partial + ((size_t)f.tile * P.n_cand) * 32 + quarter * 8 + hf * 4;
-      [[maybe_unused]] float* const part_base_tile = P.partial + ((size_t)f.tile * P.n_cand) * 32;
+      float* const part_base_tile = P.partial + ((size_t)f.tile * P.n_cand) * 32;
 
       {
         // -- one accumulator per candidate --
