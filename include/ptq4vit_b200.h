@@ -129,7 +129,8 @@ P4V_API int p4v_profile_collect(double* sweep_ms, long long* sweep_launches, dou
 /* Device self-test of the quantiser's division shortcut: evaluates round(v / delta) for n pseudo-random (v, delta)
  * pairs (plus pairs placed on and next to rounding ties) both with IEEE division, as the reference does
  * (quant_layers/linear.py:99-103 `(x / interval).round_()`), and with the reciprocal-based sequence the operand
- * image kernels use; writes the number of disagreements (must be 0). */
+ * image kernels use; writes the number of disagreements (must be 0).  Diagnostic only: unlike every other entry
+ * point it allocates 8 bytes of device memory for the duration of the call and synchronises the stream. */
 P4V_API int p4v_selftest_rint_div(unsigned long long n, unsigned long long seed, unsigned long long* mismatches, void* stream);
 
 #ifdef __cplusplus
