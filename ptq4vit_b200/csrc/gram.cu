@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(256, 2) gram_update_kernel(const GramUpdateArg
       for (int e = 0; e < 16; ++e) { xn[(mm0 + e) * KS + k] = vn[e]; xp[(mm0 + e) * KS + k] = vp[e]; }
     }
     __syncthreads();
-    constexpr int UN = 4;                                   // tokens per group; the NEXT group's e and g are in flight
+    constexpr int UN = GRAM_UN;                             // tokens per group; the NEXT group's e and g are in flight
     float en[UN], gn[UN];                                   // while the current group is multiplied
     auto fetch = [&](int mm0) {
 #pragma unroll

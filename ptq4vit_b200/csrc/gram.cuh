@@ -2,7 +2,12 @@
 #pragma once
 #include "common.cuh"
 
+#ifndef GRAM_BM
 #define GRAM_BM 64       // tokens per shared-memory chunk of the update pass
+#endif
+#ifndef GRAM_UN
+#define GRAM_UN 4        // tokens per register group of the update pass (the next group is prefetched)
+#endif
 
 struct GramUpdateArgs {
   float* E; const float* G; const float* gscale;      // [M][O] residual (in/out), gradient, power-of-two scale
