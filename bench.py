@@ -333,11 +333,15 @@ def main():
         sync_all()
         k_e2e = max(1, min(a.steps, 2))
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler2 = ClockSampler(local)
+        if rank == 0:
+            sampler2.start()
         f0.record()
         for _ in range(k_e2e):
             e2e_step()
         f1.record()
         sync_all()
+        e2e_clocks = sampler2.stop() if rank == 0 else None
         ems = f0.elapsed_time(f1)
         et = torch.tensor([ems], device=device)
         hb = torch.tensor([float(h2d), float(d2h)], device=device)
@@ -345,7 +349,7 @@ def main():
             dist.all_reduce(et, op=dist.ReduceOp.MAX); dist.all_reduce(hb)
         e2e = {"value": total_units * k_e2e / (float(et.item()) / 1e3), "unit": UNIT,
                "h2d_bytes_per_step": int(hb[0].item()), "d2h_bytes_per_step": int(hb[1].item()), "steps": k_e2e,
-               "ms_per_step": float(et.item()) / k_e2e}
+               "ms_per_step": float(et.item()) / k_e2e, "clocks": e2e_clocks}
 
     if rank != 0:
         if dist:
