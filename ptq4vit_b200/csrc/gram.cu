@@ -7,10 +7,13 @@
 // Expanding the square per output channel o with d = w_c[o,:] - w_cur[o,:] (ks numbers):
 //     sum_m (g e)^2  -  2 d . U[o]  +  d^T H[o] d ,   U[o] = sum_m g^2 e xhat ,  H[o] = sum_m g^2 xhat xhat^T .
 // All three terms are of the size of the quantisation error (no cancellation; fp32 reproduces the reference's
-// score tables to 2e-7, see tests).  H is a contraction over the TOKENS, so it runs as one tensor-core GEMM
-// (g^2)^T[O x M] . Z[M x ks(ks+1)/2] per step -- the candidates never touch TMEM or HBM again: evaluating all
-// eq_n candidates costs eq_n * O * ks^2/2 FMAs.  This removes the TMEM->register read of one 128x128 accumulator
-// per candidate and tile (64 B/clk/SM, the limit of the direct sweep).
+// score tables to 2e-7 on the CPU and <= 2.3e-5 on the GPU, see tests).  H is a contraction over the TOKENS, so it
+// runs as ONE tensor-core GEMM per round, (g^2)^T[O x M] . Z[M x n_H*ks(ks+1)/2] (gram_gemm.cu; the activations do not
+// change during the weight steps) -- the candidates never touch TMEM or HBM again: evaluating all eq_n candidates
+// costs eq_n * O * ks^2/2 FMAs.  This removes the per-candidate accumulator hand-over (TMEM -> registers, three
+// fp32 operations per output element) that bounds the slab sweep of narrow column blocks.
+// This file: token-major activations, the pair image Z, the per-step update pass (e, U, sum (g e)^2), the candidate
+// evaluation and the small reductions.
 #include "gram.cuh"
 
 void p4v_count_launch();

@@ -491,7 +491,7 @@ int search_step(const LinPlan& p, void* ws, StepRef cur, const StepRef* next, bo
 }
 
 // Whole W search of one round in normal-equation form (gram.cu): residual once, then per column block
-// update pass -> pair image -> Gram GEMM (the sweep kernel in output mode) -> candidate evaluation -> select -> commit.
+// (pair image + Gram GEMM for every column block, once) and per column block update pass -> candidate evaluation -> select -> commit.
 int gram_wsearch(const LinPlan& p, void* ws, const float* x, const float* W, const float* bias, const float* y, const float* g,
                  int h_begin, int h_end, float* score_log, cudaStream_t st) {
   int rc;
