@@ -83,6 +83,26 @@ static inline __host__ __device__ int p4v_cdiv(int a, int b) { return (a + b - 1
 static inline __host__ __device__ unsigned p4v_job_nsub(const P4VJob& j) { return j.nsub ? j.nsub : 1u; }
 static inline __host__ __device__ unsigned p4v_job_bytes(const P4VJob& j) { return (unsigned)j.kb * p4v_job_nsub(j) * P4V_TILE; }   // per operand
 
+#ifdef __CUDACC__
+// ---- exact rounding division shared by the operand-image and the Gram kernels ----
+// rintf(__fdiv_rn(v, delta)) without the general-purpose division: rcp must be __frcp_rn(delta).
+// q1 = q0 + (v - delta*q0)*rcp differs from the correctly rounded quotient by at most one ulp, so rint(q1) equals
+// rint(v/delta) unless q1 lies within a few ulps of a half-integer; those (one in ~10^4) and non-finite values
+// take the exact division.  Only valid for 2^-100 < |delta| < 2^100 (p4v_rint_div_ok, checked once per step size).
+__device__ __forceinline__ float p4v_rint_div(float v, float delta, float rcp) {
+  const float q0 = v * rcp;
+  const float q1 = fmaf(fmaf(-delta, q0, v), rcp, q0);
+  const float n = rintf(q1);
+  const float aq = fabsf(q1);
+  const float dist = fabsf(fabsf(q1 - n) - 0.5f);
+  if (!(aq <= 3.0e38f) || dist <= aq * 4.8e-7f) return rintf(__fdiv_rn(v, delta));
+  return n;
+}
+
+__device__ __forceinline__ bool p4v_rint_div_ok(float delta) { const float ad = fabsf(delta); return ad > 7.9e-31f && ad < 1.2e30f; }
+
+#endif
+
 // ---- error plumbing (host) --------------------------------------------------
 #ifdef __cplusplus
 extern "C" void p4v_set_error(const char* fmt, ...);

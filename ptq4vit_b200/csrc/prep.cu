@@ -89,20 +89,6 @@ __global__ void make_gscale_kernel(const int* key, float* gscale) {
   gscale[0] = s;
 }
 
-// rintf(__fdiv_rn(v, delta)) without the general-purpose division: rcp must be __frcp_rn(delta).
-// q1 = q0 + (v - delta*q0)*rcp differs from the correctly rounded quotient by at most one ulp, so rint(q1) equals
-// rint(v/delta) unless q1 lies within a few ulps of a half-integer; those (one in ~10^4) and non-finite values
-// take the exact division.  Only valid for 2^-100 < delta < 2^100 (checked once per plane by the caller).
-__device__ __forceinline__ float rint_div(float v, float delta, float rcp) {
-  const float q0 = v * rcp;
-  const float q1 = fmaf(fmaf(-delta, q0, v), rcp, q0);
-  const float n = rintf(q1);
-  const float aq = fabsf(q1);
-  const float dist = fabsf(fabsf(q1 - n) - 0.5f);
-  if (!(aq <= 3.0e38f) || dist <= aq * 4.8e-7f) return rintf(__fdiv_rn(v, delta));
-  return n;
-}
-
 // One thread = one (problem, 16-byte chunk, padded row) for a strided subset of the planes.  grid = (row blocks,
 // P * chunks, plane groups): rows are the fastest index so that the 16-byte stores of a warp are contiguous in the
 // image; the source values are loaded once and quantised for every plane (candidate step size) of the subset.
@@ -159,8 +145,7 @@ __global__ void quant_image_kernel(const QuantImageArgs a, int chunks_total) {
       const float split = sg.sos_part ? (a.factors ? a.factors[plane] : a.split[0]) : 0.f;
       float delta = delta0;
       if (plain && sg.fixed_delta <= 0.f && a.factors) delta = a.factors[plane] * delta0;   // fl(f_c * delta0), as the reference's candidate table
-      const float ad = fabsf(delta);
-      const bool fast = plain && ad > 7.9e-31f && ad < 1.2e30f;
+      const bool fast = plain && p4v_rint_div_ok(delta);
       const float rcp = fast ? __frcp_rn(delta) : 0.f;
 #pragma unroll
       for (int e = 0; e < epc; ++e) {
@@ -177,7 +162,7 @@ __global__ void quant_image_kernel(const QuantImageArgs a, int chunks_total) {
           } else if (sg.sos_part == 2) {
             q = fminf(fmaxf(rintf(__fdiv_rn(fminf(fmaxf(v, 0.f), split), __fdiv_rn(split, sg.qm1))), 0.f), sg.qm1);
           } else {
-            q = fminf(fmaxf(fast ? rint_div(v, delta, rcp) : rintf(__fdiv_rn(v, delta)), sg.lo), sg.hi);
+            q = fminf(fmaxf(fast ? p4v_rint_div(v, delta, rcp) : rintf(__fdiv_rn(v, delta)), sg.lo), sg.hi);
           }
           if (!(q == q)) q = 0.f;   // NaN (0/0) cannot be represented in the integer operand
         }
@@ -397,8 +382,7 @@ __global__ void rint_div_selftest_kernel(unsigned long long n, unsigned long lon
       v = __uint_as_float(__float_as_uint(v) + steps);
     }
     const float want = rintf(__fdiv_rn(v, delta));
-    const float ad = fabsf(delta);
-    const float got = (ad > 7.9e-31f && ad < 1.2e30f) ? rint_div(v, delta, __frcp_rn(delta)) : want;
+    const float got = p4v_rint_div_ok(delta) ? p4v_rint_div(v, delta, __frcp_rn(delta)) : want;
     if (!(want == got) && !(want != want && got != got)) ++bad;
   }
   if (bad) atomicAdd(mismatches, bad);
