@@ -182,7 +182,7 @@ def linear_calibrate(sp: LinearSpec, W, bias, x, raw_out, raw_grad, return_score
     """calibration_step2 of PTQSLBatchingQuantLinear (linear.py:536-555) and of
     PostGeluPTQSLBatchingQuantLinear (same driver, overridden pieces)."""
     w_int, a_int = linear_initial_intervals(sp, W, x)
-    f = candidate_factors(sp.eq_alpha, sp.eq_beta, sp.eq_n)
+    f = candidate_factors(sp.eq_alpha, sp.eq_beta, sp.eq_n).to(W.device)
     w_cands = f.view(-1, 1, 1, 1, 1) * w_int.unsqueeze(0)       # linear.py:544
     a_cands = f.view(1, 1, -1) * a_int.unsqueeze(-1)            # linear.py:545
     log = []
@@ -306,13 +306,13 @@ def matmul_calibrate(sp: MatMulSpec, A, B, raw_out, raw_grad, return_scores=Fals
     """calibration_step2 of PTQSLBatchingQuantMatMul (matmul.py:565-576) and of
     SoSPTQSLBatchingQuantMatMul (matmul.py:633-644)."""
     A_int, B_int = matmul_initial_intervals(sp, A, B)
-    f = candidate_factors(sp.eq_alpha, sp.eq_beta, sp.eq_n).view(-1, 1, 1, 1, 1, 1, 1, 1)
+    f = candidate_factors(sp.eq_alpha, sp.eq_beta, sp.eq_n).view(-1, 1, 1, 1, 1, 1, 1, 1).to(A.device)
     B_cands = f * B_int.unsqueeze(0)
     log = []
     if sp.sos:
-        split = torch.tensor(0.01)
+        split = torch.tensor(0.01, device=A.device)
         A_int = split / (sp.A_qmax - 1)
-        split_cands = torch.tensor([2 ** (-i) for i in range(20)], dtype=torch.float32)  # matmul.py:636
+        split_cands = torch.tensor([2 ** (-i) for i in range(20)], dtype=torch.float32, device=A.device)  # matmul.py:636
         for _ in range(sp.search_round):
             split, A_int, s1 = sos_search_split(sp, A, B, raw_out, raw_grad, split_cands)
             B_int, s2 = matmul_search_B(sp, A, B, raw_out, raw_grad, A_int, B_int, B_cands, split)

@@ -1,5 +1,6 @@
 """Operator factory with the reference's contract (configs/PTQ4ViT.py:1-80): module-level
 kwargs dicts that experiment code mutates in place, and get_module(module_type, *args)."""
+from ..quant_layers.conv import ChannelwiseBatchingQuantConv2d
 from ..quant_layers.linear import PTQSLBatchingQuantLinear, PostGeluPTQSLBatchingQuantLinear
 from ..quant_layers.matmul import PTQSLBatchingQuantMatMul, SoSPTQSLBatchingQuantMatMul
 
@@ -23,9 +24,8 @@ ptqsl_matmul_kwargs = {"metric": "hessian", "eq_alpha": 0.01, "eq_beta": 1.2, "e
 
 def get_module(module_type, *args, **kwargs):
     if module_type == "qconv":
-        # reference: ChannelwiseBatchingQuantConv2d (configs/PTQ4ViT.py:52-54); the patch-embedding conv is
-        # outside the hot path this package covers -- the wrapper leaves it in FP32.
-        raise NotImplementedError("qconv (patch-embedding conv search) is out of scope of ptq4vit_b200")
+        kwargs.update(ptqsl_conv2d_kwargs)
+        module = ChannelwiseBatchingQuantConv2d(*args, **kwargs, w_bit=w_bit["qconv"], a_bit=32)  # activation quantization off
     elif "qlinear" in module_type:
         kwargs.update(ptqsl_linear_kwargs)
         if module_type == "qlinear_qkv":

@@ -7,7 +7,13 @@
 // from L2 feeds three tensor-core passes, and the 128x256 output tile halves the operand bytes per flop once more:
 // 48 KB per 768 MMA cycles = 62 B/clk/SM (the per-step 128x128 three-pass version needed 125 B/clk/SM and ran at the
 // L2->SM limit with 90 of 148 SMs).
-// Roles: warp 0 = bulk-copy producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..5 = epilogue (TMEM -> H, fp32).
+// The tensor core adds into the fp32 accumulator with truncation, so a long contraction of same-signed terms (the
+// diagonal of H: 6304 tokens x 3 products) drifts by ~1e-5 relative (measured against an fp64 evaluation; it was the
+// whole 2e-5..2e-4 score error of the normal-equation steps).  The contraction is therefore cut into splits of
+// `kSplitChunks` stages (256 tokens): each split accumulates in its own TMEM slot and the epilogue adds the splits in
+// registers with round-to-nearest fp32 adds.  The epilogue pass of a split (128 columns per thread) takes ~300 cycles
+// against ~6000 cycles of MMAs per split.
+// Roles: warp 0 = bulk-copy producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..9 = epilogue (TMEM -> registers -> H).
 #include "gram.cuh"
 #include <cstdio>
 
@@ -16,7 +22,8 @@ int p4v_num_sms();
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 64 + 256;
+constexpr int kSplitChunks = 8;                                     // stages (64 B of K = 32 tokens each) per accumulation split
 constexpr int kStages = 4;
 constexpr uint32_t kStageKB = 64;                                   // bytes of K per row and stage
 constexpr uint32_t kRTerm = kStageKB * 128, kCTerm = kStageKB * 256;  // bytes of one term tile in a stage
@@ -105,7 +112,7 @@ __global__ void __launch_bounds__(kThreads, 1) gram_gemm_kernel(const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(&S.full[i], 1); mbar_init(&S.empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&S.acc_full[i], 1); mbar_init(&S.acc_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&S.acc_full[i], 1); mbar_init(&S.acc_empty[i], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -144,9 +151,10 @@ __global__ void __launch_bounds__(kThreads, 1) gram_gemm_kernel(const __grid_con
     // ---------------- MMA issuer ----------------
     uint32_t stage = 0, phase = 0, slot = 0, sphase = 0;
     for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
-      mbar_wait(&S.acc_empty[slot], sphase ^ 1);
-      const uint32_t d = tmem + slot * kAccCols;
       for (int ch = 0; ch < n_chunks; ++ch) {
+        const bool first = ch % kSplitChunks == 0, last = (ch % kSplitChunks == kSplitChunks - 1) || ch == n_chunks - 1;
+        if (first) mbar_wait(&S.acc_empty[slot], sphase ^ 1);
+        const uint32_t d = tmem + slot * kAccCols;
         const uint32_t k0 = ch * kStageKB, kb = (term - k0 < kStageKB) ? term - k0 : kStageKB;
         mbar_wait(&S.full[stage], phase);
         tc_fence_after();
@@ -156,41 +164,50 @@ __global__ void __launch_bounds__(kThreads, 1) gram_gemm_kernel(const __grid_con
           const uint64_t chi = make_desc(s0 + 2 * kRTerm, 256), clo = make_desc(s0 + 2 * kRTerm + kCTerm, 256);
           for (uint32_t ks = 0; ks * 32 < kb; ++ks) {          // one K step = 16 bf16 = two 16-byte chunks
             const uint64_t ra = ks * ((2u * 128 * 16) >> 4), ca = ks * ((2u * 256 * 16) >> 4);
-            umma_bf16_n256(d, rhi + ra, chi + ca, (ch | ks) ? 1u : 0u);
+            umma_bf16_n256(d, rhi + ra, chi + ca, (!first || ks) ? 1u : 0u);
             umma_bf16_n256(d, rhi + ra, clo + ca, 1u);
             umma_bf16_n256(d, rlo + ra, chi + ca, 1u);
           }
           tc_commit(&S.empty[stage]);
-          if (ch == n_chunks - 1) tc_commit(&S.acc_full[slot]);
+          if (last) tc_commit(&S.acc_full[slot]);
         }
         if (++stage == kStages) { stage = 0; phase ^= 1; }
+        if (last) { if (++slot == 2) { slot = 0; sphase ^= 1; } }
       }
-      if (++slot == 2) { slot = 0; sphase ^= 1; }
     }
   } else {
-    // ---------------- epilogue: TMEM -> H ----------------
-    const int quarter = warp & 3;
+    // ---------------- epilogue: TMEM -> registers (sum of the splits) -> H ----------------
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;             // column half: 128 of the tile's 256 columns
+    const int n_splits = (n_chunks + kSplitChunks - 1) / kSplitChunks;
     uint32_t slot = 0, sphase = 0;
     for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
       const int o = (t % a.tiles_o) * 128 + quarter * 32 + lane;
-      float* hrow = a.H + (size_t)o * a.ldH + (size_t)(t / a.tiles_o) * 256;
-      mbar_wait(&S.acc_full[slot], sphase);
-      tc_fence_after();
-      const uint32_t tb = tmem + ((uint32_t)(quarter * 32) << 16) + slot * kAccCols;
-#pragma unroll 1
-      for (int c = 0; c < 256; c += 32) {
-        float v[32];
-        tmem_ld32(tb + c, v);
-        tmem_wait_ld();
-        if (o < a.O) {
+      float* hrow = a.H + (size_t)o * a.ldH + (size_t)(t / a.tiles_o) * 256 + half * 128;
+      float acc[128];
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(hrow + c + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      for (int j = 0; j < 128; ++j) acc[j] = 0.f;
+      for (int sp = 0; sp < n_splits; ++sp) {
+        mbar_wait(&S.acc_full[slot], sphase);
+        tc_fence_after();
+        const uint32_t tb = tmem + ((uint32_t)(quarter * 32) << 16) + slot * kAccCols + half * 128;
+#pragma unroll
+        for (int c = 0; c < 128; c += 32) {
+          float v[32];
+          tmem_ld32(tb + c, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[c + j] += v[j];
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&S.acc_empty[slot]);
+        if (++slot == 2) { slot = 0; sphase ^= 1; }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&S.acc_empty[slot]);
-      if (++slot == 2) { slot = 0; sphase ^= 1; }
+      if (o < a.O) {
+#pragma unroll
+        for (int j = 0; j < 128; j += 4) *reinterpret_cast<float4*>(hrow + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+      }
     }
   }
   tc_fence_before();

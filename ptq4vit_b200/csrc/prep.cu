@@ -1,6 +1,7 @@
 #include "prep.cuh"
 #include "../../include/ptq4vit_b200.h"
 #include <math.h>
+#include <stdlib.h>
 
 void p4v_count_launch();
 
@@ -68,10 +69,16 @@ __global__ void group_absmax_kernel(const float* __restrict__ src, long long pro
   }
 }
 
-__global__ void keys_to_delta_kernel(const int* keys, int n, float denom, float* d0, float* d1) {
+// The reference divides the block maxima by the Python scalar (qmax - 0.5) (linear.py:385, :395; matmul.py:424-436).
+// On the GPU -- where the reference's Batching classes always run -- torch's true-divide by a CPU scalar is a
+// multiplication by the fp32 reciprocal (ATen BinaryDivTrueKernel.cu), which differs from the IEEE quotient by one ulp
+// for about a third of the inputs; a one-ulp step size moves the rounding of ~1e-5 of the quantised elements and with
+// 32x32 weight blocks that is visible in the scores (measured: up to 2.6e-3 of an entry).  ieee_div = 1 selects the IEEE
+// quotient instead (what torch computes on the CPU; the CPU-made golden vectors).
+__global__ void keys_to_delta_kernel(const int* keys, int n, float denom, int ieee_div, float* d0, float* d1) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
-    float v = __fdiv_rn(key2f(keys[i]), denom);
+    float v = ieee_div ? __fdiv_rn(key2f(keys[i]), denom) : __fmul_rn(key2f(keys[i]), __fdiv_rn(1.f, denom));
     d0[i] = v;
     if (d1) d1[i] = v;
   }
@@ -147,6 +154,7 @@ __global__ void quant_image_kernel(const QuantImageArgs a, int chunks_total) {
       if (plain && sg.fixed_delta <= 0.f && a.factors) delta = a.factors[plane] * delta0;   // fl(f_c * delta0), as the reference's candidate table
       const bool fast = plain && p4v_rint_div_ok(delta);
       const float rcp = fast ? __frcp_rn(delta) : 0.f;
+      const float rcp_fixed = sg.fixed_delta > 0.f ? __fdiv_rn(1.f, sg.fixed_delta) : 0.f;
 #pragma unroll
       for (int e = 0; e < epc; ++e) {
         const int kk = chunk * epc + e;
@@ -162,7 +170,12 @@ __global__ void quant_image_kernel(const QuantImageArgs a, int chunks_total) {
           } else if (sg.sos_part == 2) {
             q = fminf(fmaxf(rintf(__fdiv_rn(fminf(fmaxf(v, 0.f), split), __fdiv_rn(split, sg.qm1))), 0.f), sg.qm1);
           } else {
-            q = fminf(fmaxf(fast ? p4v_rint_div(v, delta, rcp) : rintf(__fdiv_rn(v, delta)), sg.lo), sg.hi);
+            // A step size that the reference holds as a Python scalar (the constant negative-part step of the post-GELU
+            // twin quantizer, linear.py:574, :605) is divided by as `x * (1/delta)` on the GPU: torch's CUDA true-divide
+            // multiplies by the fp32 reciprocal when the divisor is a CPU scalar (ATen BinaryDivTrueKernel.cu).  Tensors
+            // (every searched step size) take the IEEE division.
+            if (sg.fixed_delta > 0.f && !a.ieee_div) q = fminf(fmaxf(rintf(v * rcp_fixed), sg.lo), sg.hi);
+            else q = fminf(fmaxf(fast ? p4v_rint_div(v, delta, rcp) : rintf(__fdiv_rn(v, delta)), sg.lo), sg.hi);
           }
           if (!(q == q)) q = 0.f;   // NaN (0/0) cannot be represented in the integer operand
         }
@@ -346,8 +359,12 @@ int p4v_group_absmax(const float* src, long long prob_elems, int P, int n_groups
   return 0;
 }
 
+int p4v_scalar_div_ieee() {
+  const char* e = getenv("P4V_SCALAR_DIV");      // "ieee": reference executed on the CPU; default: reference executed on the GPU
+  return (e && e[0] == 'i') ? 1 : 0;
+}
 int p4v_keys_to_delta(const int* keys, int n, float denom, float* d0, float* d1, cudaStream_t st) {
-  keys_to_delta_kernel<<<p4v_cdiv(n, 128), 128, 0, st>>>(keys, n, denom, d0, d1); p4v_count_launch();
+  keys_to_delta_kernel<<<p4v_cdiv(n, 128), 128, 0, st>>>(keys, n, denom, p4v_scalar_div_ieee(), d0, d1); p4v_count_launch();
   P4V_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -403,7 +420,9 @@ extern "C" int p4v_selftest_rint_div(unsigned long long n, unsigned long long se
   return 0;
 }
 
-int p4v_quant_image(const QuantImageArgs& a, cudaStream_t st) {
+int p4v_quant_image(const QuantImageArgs& a_in, cudaStream_t st) {
+  QuantImageArgs a = a_in;
+  a.ieee_div = p4v_scalar_div_ieee();
   const int chunks_total = (int)(a.tile_bytes / P4V_TILE / 16);     // every segment is padded to 32 B
   const int rows_pad = a.tiles * P4V_TILE;
   if (rows_pad == 0 || chunks_total == 0 || a.n_planes == 0 || a.P == 0) return 0;

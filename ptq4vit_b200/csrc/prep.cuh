@@ -30,6 +30,7 @@ struct QuantImageArgs {
   int is_int8;
   const float* split;    // sos: device scalar split point for the current image (candidate planes use factors[plane])
   const float* presc;    // optional device scalar multiplied into the source before `square`
+  int ieee_div;          // filled by p4v_quant_image: Python-scalar step sizes divide the IEEE way (see keys_to_delta)
 };
 int p4v_quant_image(const QuantImageArgs& a, cudaStream_t st);
 
@@ -40,6 +41,7 @@ int p4v_block_max(const float* src, long long ld, int rows, int row_block, int n
 int p4v_group_absmax(const float* src, long long prob_elems, int P, int n_groups, int* keys, cudaStream_t st);
 int p4v_keys_reset(int* keys, int n, cudaStream_t st);
 // delta[i] = key_to_float(keys[i]) / denom ; optionally copy to a second array
+int p4v_scalar_div_ieee();
 int p4v_keys_to_delta(const int* keys, int n, float denom, float* d0, float* d1, cudaStream_t st);
 // gscale = 2^-floor(log2(max|g|)) (1 if max is 0 / non-finite)
 int p4v_make_gscale(const int* key, float* gscale, cudaStream_t st);

@@ -2,3 +2,4 @@ from .linear import (MinMaxQuantLinear, PTQSLQuantLinear, PostGeluPTQSLQuantLine
                      PostGeluPTQSLBatchingQuantLinear)
 from .matmul import (MinMaxQuantMatMul, PTQSLQuantMatMul, SoSPTQSLQuantMatMul, PTQSLBatchingQuantMatMul,
                      SoSPTQSLBatchingQuantMatMul)
+from .conv import MinMaxQuantConv2d, PTQSLQuantConv2d, ChannelwiseBatchingQuantConv2d

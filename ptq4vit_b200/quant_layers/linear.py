@@ -20,6 +20,22 @@ def _flat2d(t):
     return t.reshape(-1, t.shape[-1]).contiguous().float()
 
 
+class _QuantLinearFn(torch.autograd.Function):
+    """Keeps the native quantized forward inside autograd.  In the reference `quant_forward` is
+    F.linear(x_sim, w_sim, bias) with x_sim / w_sim built by `.round_()` (linear.py:46-67), whose derivative is zero:
+    no gradient reaches x or the weight, but the output carries a grad_fn (through the bias / weight Parameters), so
+    that with sequential=True the gradient hooks of the modules BEHIND an already-quantized layer still fire
+    (utils/quant_calib.py:330-341).  Same here: the output requires grad, every input gradient is zero."""
+
+    @staticmethod
+    def forward(ctx, module, x, weight, bias):
+        return module._quant_forward_native(x)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        return None, None, None, None
+
+
 class MinMaxQuantLinear(nn.Linear):
     """reference: quant_layers/linear.py:6-92"""
 
@@ -93,6 +109,11 @@ class MinMaxQuantLinear(nn.Linear):
     def quant_forward(self, x):
         """reference: linear.py:62-67 -- fq(x) @ fq(W)^T + b on the tensor cores."""
         assert self.calibrated is not None, f"You should run calibrate_forward before run quant_forward for {self}"
+        if torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad):
+            return _QuantLinearFn.apply(self, x, self.weight, self.bias)
+        return self._quant_forward_native(x)
+
+    def _quant_forward_native(self, x):
         dev = self._device()
         x2 = _flat2d(x.to(dev))
         d = self._desc(x2.shape[0], 1)

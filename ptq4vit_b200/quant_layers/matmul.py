@@ -12,6 +12,20 @@ from torch import nn
 from .. import _lib
 
 
+class _QuantMatMulFn(torch.autograd.Function):
+    """The native quantized product inside autograd: the reference's quant_forward (matmul.py:40-45) rounds both
+    operands in place, so no gradient flows to A or B, but the output still has a grad_fn whenever an input requires
+    grad -- which the gradient hooks of later modules rely on with sequential=True (utils/quant_calib.py:330-341)."""
+
+    @staticmethod
+    def forward(ctx, module, A, B):
+        return module._quant_forward_native(A, B)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        return None, None, None
+
+
 class MinMaxQuantMatMul(nn.Module):
     """reference: quant_layers/matmul.py:8-60"""
     sos = False
@@ -85,6 +99,11 @@ class MinMaxQuantMatMul(nn.Module):
     def quant_forward(self, A, B):
         """reference: matmul.py:40-45 / :140-145 -- fq(A) @ fq(B) on the tensor cores."""
         assert self.calibrated is not None, f"You should run calibrate_forward before run quant_forward for {self}"
+        if torch.is_grad_enabled() and (A.requires_grad or B.requires_grad):
+            return _QuantMatMulFn.apply(self, A, B)
+        return self._quant_forward_native(A, B)
+
+    def _quant_forward_native(self, A, B):
         A_, B_ = self._cuda(A), self._cuda(B)
         dev = A_.device
         d = self._desc(A_, B_)

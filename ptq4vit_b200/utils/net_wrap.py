@@ -20,9 +20,13 @@ def wrap_modules_in_net(net, cfg, wrap_conv=False):
         if father is None:
             continue
         if isinstance(m, nn.Conv2d):
-            if wrap_conv:
-                raise NotImplementedError("patch-embedding conv search is out of scope (SURVEY.md 8f)")
-            continue          # the embedding conv stays FP32
+            if not wrap_conv:
+                continue      # the embedding conv stays FP32
+            new_m = cfg.get_module("qconv", m.in_channels, m.out_channels, m.kernel_size, m.stride, m.padding, m.dilation,
+                                   m.groups, m.bias is not None, m.padding_mode)
+            new_m.weight.data = m.weight.data
+            new_m.bias = m.bias
+            new_m.to(m.weight.device)
         if isinstance(m, nn.Linear):
             new_m = cfg.get_module(MODULE_TYPES[leaf], m.in_features, m.out_features)
             new_m.weight.data = m.weight.data

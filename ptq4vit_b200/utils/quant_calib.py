@@ -14,23 +14,40 @@
 * multi-GPU: modules are independent => static LPT sharding over ranks, every rank captures,
   searches its share, and one all_gather of the chosen step sizes ends the job.
 """
-import math
+import time
 
 import torch
 import torch.nn.functional as F
 
-from ..quant_layers.linear import MinMaxQuantLinear
-from ..quant_layers.matmul import MinMaxQuantMatMul
+from ..quant_layers.conv import MinMaxQuantConv2d
+from ..quant_layers.linear import MinMaxQuantLinear, PTQSLBatchingQuantLinear
+from ..quant_layers.matmul import MinMaxQuantMatMul, PTQSLBatchingQuantMatMul
 
 
 # ---------------------------------------------------------------- hooks (device resident)
+def _keep_grad(module, output):
+    """The gradient of the loss w.r.t. the module output (what the reference's `register_backward_hook(grad_hook)`
+    receives as grad_output[0], quant_calib.py:173-176, :330), taken with a tensor hook: it fires whenever a
+    gradient reaches the output, independent of which inputs require grad."""
+    if not (torch.is_grad_enabled() and output.requires_grad):
+        return
+
+    def _hook(grad):
+        if module.raw_grad is None:
+            module.raw_grad = []
+        module.raw_grad.append(grad.detach())
+    output.register_hook(_hook)
+
+
 def grad_hook(module, grad_input, grad_output):
+    """reference: quant_calib.py:173-176 (kept for API parity; the calibrators below use tensor hooks)."""
     if module.raw_grad is None:
         module.raw_grad = []
     module.raw_grad.append(grad_output[0].detach())
 
 
 def linear_forward_hook(module, input, output):
+    """reference: quant_calib.py:178-183 (tensors stay on the device)."""
     if module.raw_input is None:
         module.raw_input = []
     if module.raw_out is None:
@@ -39,7 +56,11 @@ def linear_forward_hook(module, input, output):
     module.raw_out.append(output.detach())
 
 
+conv2d_forward_hook = linear_forward_hook          # reference: quant_calib.py:185-190
+
+
 def matmul_forward_hook(module, input, output):
+    """reference: quant_calib.py:192-199"""
     if module.raw_input is None:
         module.raw_input = [[], []]
     if module.raw_out is None:
@@ -50,7 +71,7 @@ def matmul_forward_hook(module, input, output):
 
 
 def _cat_captured(module):
-    if isinstance(module, MinMaxQuantLinear):
+    if isinstance(module, (MinMaxQuantLinear, MinMaxQuantConv2d)):
         module.raw_input = torch.cat(module.raw_input, dim=0)
         module.raw_out = torch.cat(module.raw_out, dim=0)
     if isinstance(module, MinMaxQuantMatMul):
@@ -61,15 +82,33 @@ def _cat_captured(module):
 
 
 # ---------------------------------------------------------------- work model + sharding
-def module_cost(module, n_img, tokens_hint=197):
-    """Relative cost of one module's search in candidate-GEMM operations."""
+def module_cost(module, n_img, shapes=None, tokens_hint=197):
+    """Relative cost of one module's search (executed work of the CUDA path, not full-GEMM units):
+    Linear  : rounds * eq_n * 2*M*K*O * (1 [all weight steps together: each multiplies one K slab] + n_a [activation steps])
+    MatMul  : rounds * 2 * eq_n * 2*b*H*S1*S2*S3
+    `shapes` = per-image input shapes recorded by a probe forward ({"x": (tokens.., K)} / {"A": (H,S1,S2), "B": (H,S2,S3)})."""
+    rounds = getattr(module, "search_round", 1)
+    eq_n = getattr(module, "eq_n", 1)
     if isinstance(module, MinMaxQuantLinear):
-        rounds = getattr(module, "search_round", 1)
-        units = rounds * (getattr(module, "n_H", 1) + getattr(module, "n_a", 1)) * getattr(module, "eq_n", 1)
-        return float(units) * 2.0 * n_img * tokens_hint * module.in_features * module.out_features / max(1, getattr(module, "n_H", 1))
+        rows = tokens_hint
+        if shapes is not None and "x" in shapes:
+            rows = 1
+            for s in shapes["x"][:-1]:
+                rows *= int(s)
+        gemm = 2.0 * n_img * rows * module.in_features * module.out_features
+        return float(rounds * eq_n) * gemm * (1.0 + getattr(module, "n_a", 1))
+    if isinstance(module, MinMaxQuantConv2d):
+        return 0.0 if shapes is None else float(rounds * eq_n) * 2.0 * n_img * shapes.get("conv_macs", 0.0)
     if isinstance(module, MinMaxQuantMatMul):
-        rounds = getattr(module, "search_round", 1)
-        return float(rounds * 2 * getattr(module, "eq_n", 1)) * 2.0 * n_img * 12 * tokens_hint * tokens_hint * 64
+        if shapes is not None and "A" in shapes:
+            H, S1, S2 = [int(s) for s in shapes["A"][-3:]]
+            S3 = int(shapes["B"][-1])
+            lead = 1
+            for s in shapes["A"][:-3]:
+                lead *= int(s)
+        else:
+            lead, H, S1, S2, S3 = 1, 12, tokens_hint, 64, tokens_hint
+        return float(rounds * 2 * eq_n) * 2.0 * n_img * lead * H * S1 * S2 * S3
     return 0.0
 
 
@@ -85,18 +124,25 @@ def shard_modules(names, costs, world_size):
     return owner
 
 
+def _flat_results(module):
+    if isinstance(module, (MinMaxQuantLinear, MinMaxQuantConv2d)):
+        vals = [module.w_interval]
+        if module.a_interval is not None:
+            vals.append(module.a_interval)
+    else:
+        vals = [module.A_interval, module.B_interval]
+        if getattr(module, "sos", False):
+            vals.append(module.split)
+    dev = None
+    for v in vals:
+        if torch.is_tensor(v) and v.device.type == "cuda":
+            dev = v.device
+    return [torch.as_tensor(v, dtype=torch.float32, device=dev).reshape(-1) for v in vals]
+
+
 def pack_result(module, width):
     """Flatten a calibrated module's step sizes into a fixed-width fp32 row for the all_gather."""
-    vals = []
-    if isinstance(module, MinMaxQuantLinear):
-        vals += [torch.as_tensor(module.w_interval, dtype=torch.float32).reshape(-1),
-                 torch.as_tensor(module.a_interval, dtype=torch.float32).reshape(-1)]
-    else:
-        vals += [torch.as_tensor(module.A_interval, dtype=torch.float32).reshape(-1),
-                 torch.as_tensor(module.B_interval, dtype=torch.float32).reshape(-1)]
-        if getattr(module, "sos", False):
-            vals.append(torch.as_tensor(module.split, dtype=torch.float32).reshape(-1))
-    flat = torch.cat([v.to(vals[0].device) for v in vals])
+    flat = torch.cat(_flat_results(module))
     assert flat.numel() <= width, f"result of {type(module).__name__} does not fit the gather row ({flat.numel()} > {width})"
     row = torch.zeros(width, dtype=torch.float32, device=flat.device)
     row[:flat.numel()] = flat
@@ -105,7 +151,10 @@ def pack_result(module, width):
 
 def unpack_result(module, row, heads=None):
     """Inverse of pack_result (the module's static block structure gives the split points)."""
-    if isinstance(module, MinMaxQuantLinear):
+    if isinstance(module, MinMaxQuantConv2d):
+        nw = module.out_channels
+        module.w_interval = row[:nw].clone().view(nw, 1, 1, 1)
+    elif isinstance(module, MinMaxQuantLinear):
         nw = module.n_V * module.n_H
         module.w_interval = row[:nw].clone().view(module.n_V, 1, module.n_H, 1)
         module.a_interval = row[nw:nw + module.n_a].clone().view(module.n_a, 1)
@@ -118,20 +167,22 @@ def unpack_result(module, row, heads=None):
         else:
             module.A_interval = row[:H].clone().view(1, H, 1, 1, 1, 1, 1)
             module.B_interval = row[H:2 * H].clone().view(1, H, 1, 1, 1, 1, 1)
+        module.n_G_A = module.n_G_B = H
     module.calibrated = True
 
 
 def result_width(modules):
     w = 1
     for m in modules:
-        if isinstance(m, MinMaxQuantLinear):
+        if isinstance(m, MinMaxQuantConv2d):
+            w = max(w, m.out_channels)
+        elif isinstance(m, MinMaxQuantLinear):
             w = max(w, m.n_V * m.n_H + m.n_a)
         else:
             w = max(w, 2 * 64 + 1)        # up to 64 heads + split
     return w
 
 
-# ---------------------------------------------------------------- calibrators
 # ---------------------------------------------------------------- host-resident captures
 def search_from_host(items, device, out_host=None):
     """Search a list of modules whose captured tensors live in (pinned) HOST memory, as the reference's calibrators
@@ -140,9 +191,6 @@ def search_from_host(items, device, out_host=None):
     items: [(module, {"x"|"A","B", "y", "g": pinned cpu tensors})].  The host->device copies of module i+1 run on a
     side stream while module i searches; the chosen step sizes are copied back asynchronously into pinned buffers and
     one synchronisation ends the call.  Returns (h2d_bytes, d2h_bytes)."""
-    import os, time
-    dbg = os.environ.get("P4V_E2E_DEBUG")
-    t_stage = t_cal = t_out = 0.0
     copy_stream = torch.cuda.Stream(device=device)
     main = torch.cuda.current_stream(device)
     h2d = d2h = 0
@@ -158,9 +206,7 @@ def search_from_host(items, device, out_host=None):
     nxt = stage(0) if items else None
     for i, (m, hb) in enumerate(items):
         dev, ev = nxt
-        t0 = time.perf_counter()
         nxt = stage(i + 1) if i + 1 < len(items) else None
-        t_stage += time.perf_counter() - t0
         main.wait_event(ev)
         for v in dev.values():
             v.record_stream(main)
@@ -169,27 +215,19 @@ def search_from_host(items, device, out_host=None):
             m.raw_input, m.raw_out, m.raw_grad = dev["x"], dev["y"], dev["g"]
         else:
             m.raw_input, m.raw_out, m.raw_grad = [dev["A"], dev["B"]], dev["y"], dev["g"]
-        t0 = time.perf_counter()
         with torch.no_grad():
             m.calibration_step2()
-        t_cal += time.perf_counter() - t0
-        t0 = time.perf_counter()
         m.raw_input = m.raw_out = m.raw_grad = None
-        outs = [m.w_interval, m.a_interval] if "x" in dev else [torch.as_tensor(m.A_interval, device=device), m.B_interval]
-        for j, o in enumerate(outs):
-            o = torch.as_tensor(o, device=device).detach().reshape(-1).float()
+        for j, o in enumerate(_flat_results(m)):
             buf = torch.empty(o.numel(), dtype=torch.float32, pin_memory=True) if out_host is None else out_host[i][j]
-            buf.copy_(o, non_blocking=True)
+            buf.copy_(o.detach(), non_blocking=True)
             results.append(buf)
             d2h += o.numel() * 4
-        t_out += time.perf_counter() - t0
-    t0 = time.perf_counter()
     main.synchronize()
-    if dbg:
-        print(f"[search_from_host] host time: stage {t_stage:.3f}s calibrate {t_cal:.3f}s outputs {t_out:.3f}s final sync {time.perf_counter() - t0:.3f}s", flush=True)
     return h2d, d2h
 
 
+# ---------------------------------------------------------------- calibrators
 class QuantCalibrator():
     """reference: utils/quant_calib.py:9-171"""
 
@@ -199,27 +237,106 @@ class QuantCalibrator():
         self.calib_loader = calib_loader
         self.sequential = sequential
         self.calibrated = False
-        self.batch_size = getattr(calib_loader, "batch_size", 1)   # the reference forgets this attribute (quant_calib.py:131)
+        self.batch_size = getattr(calib_loader, "batch_size", None) or 1   # the reference forgets this attribute (quant_calib.py:131)
 
     def _device(self):
         return next(self.net.parameters()).device
 
-    def quant_calib(self):
-        """reference: quant_calib.py:95-104 (step1: collect, step2: per-module search on the cached tensors)"""
+    def _loader_batches(self):
+        for item in self.calib_loader:
+            inp = item[0] if isinstance(item, (tuple, list)) else item
+            yield inp
+
+    def _run_net_no_grad(self):
+        dev = self._device()
+        with torch.no_grad():
+            for inp in self._loader_batches():
+                self.net(inp.to(dev))
+
+    def sequential_quant_calib(self):
+        """reference: quant_calib.py:28-55 -- two sweeps over the calibration data; in the second one every module
+        searches its step sizes on the (already quantized) activations that reach it and forwards its quantized output."""
+        n_calibration_steps = 2
+        for step in range(n_calibration_steps):
+            for name, module in self.wrapped_modules.items():
+                if hasattr(module, "calibrated"):
+                    if step == 1:
+                        module.mode = "raw"
+                    elif step == 2:        # unreachable, as in the reference (:39-42)
+                        module.mode = "quant_forward"
+                else:
+                    module.mode = f"calibration_step{step + 1}"
+            self._run_net_no_grad()
+        for name, module in self.wrapped_modules.items():
+            module.mode = "quant_forward"
+        torch.cuda.empty_cache()
+
+    def parallel_quant_calib(self):
+        """reference: quant_calib.py:57-93 -- step 1 collects every module's raw input/output in one sweep,
+        step 2 searches each module on its own FP32 tensors."""
         for name, module in self.wrapped_modules.items():
             module.mode = "raw" if hasattr(module, "calibrated") else "calibration_step1"
-        with torch.no_grad():
-            for inp, target in self.calib_loader:
-                self.net(inp.to(self._device()))
+        self._run_net_no_grad()
+        dev = self._device()
         for name, module in self.wrapped_modules.items():
             if hasattr(module, "calibrated"):
                 continue
             module.mode = "calibration_step2"
             with torch.no_grad():
-                if isinstance(module, MinMaxQuantLinear):
-                    module.forward(module.raw_input.to(self._device()))
+                if isinstance(module, (MinMaxQuantLinear, MinMaxQuantConv2d)):
+                    module.forward(module.raw_input.to(dev))
                 elif isinstance(module, MinMaxQuantMatMul):
-                    module.forward(module.raw_input[0].to(self._device()), module.raw_input[1].to(self._device()))
+                    module.forward(module.raw_input[0].to(dev), module.raw_input[1].to(dev))
+        for name, module in self.wrapped_modules.items():
+            module.mode = "quant_forward"
+        torch.cuda.empty_cache()
+
+    def quant_calib(self):
+        """reference: quant_calib.py:95-104"""
+        if self.sequential:
+            self.sequential_quant_calib()
+        else:
+            self.parallel_quant_calib()
+        self.calibrated = True
+
+    # -- shared by the batching drivers
+    def _forward_hooks_for(self, module, want_grad):
+        hooks = []
+        if isinstance(module, MinMaxQuantLinear):
+            hooks.append(module.register_forward_hook(linear_forward_hook))
+        if isinstance(module, MinMaxQuantConv2d):
+            hooks.append(module.register_forward_hook(conv2d_forward_hook))
+        if isinstance(module, MinMaxQuantMatMul):
+            hooks.append(module.register_forward_hook(matmul_forward_hook))
+        if want_grad:
+            hooks.append(module.register_forward_hook(lambda mod, inp, out: _keep_grad(mod, out)))
+        return hooks
+
+    def _mini_batches(self):
+        """(offset of the mini-batch inside the calibration set, images) in the reference's order
+        (quant_calib.py:130-134 / :332-335)."""
+        off = 0
+        for inp in self._loader_batches():
+            n = inp.shape[0]
+            for batch_st in range(0, n, self.batch_size):
+                yield off + batch_st, inp[batch_st:batch_st + self.batch_size]
+            off += n
+
+    def batching_quant_calib(self):
+        """reference: quant_calib.py:106-171 -- forward-only capture per module, then calibration_step2() on the
+        cached tensors (metrics that need no gradient)."""
+        dev = self._device()
+        for name, module in self.wrapped_modules.items():
+            hooks = self._forward_hooks_for(module, want_grad=False)
+            with torch.no_grad():
+                for _, inp_ in self._mini_batches():
+                    self.net(inp_.to(dev))
+            _cat_captured(module)
+            for hook in hooks:
+                hook.remove()
+            with torch.no_grad():
+                module.calibration_step2()
+            module.mode = "quant_forward" if self.sequential else "raw"
         for name, module in self.wrapped_modules.items():
             module.mode = "quant_forward"
         self.calibrated = True
@@ -236,49 +353,77 @@ class HessianQuantCalibrator(QuantCalibrator):
         self.distributed = distributed
         self.target_noise = target_noise     # synthetic benches: perturb the KL target so that gradients are not ~0
         self.timings = {}
+        self.keep_captured = None            # tests: a dict to receive {name: captured tensors} before they are consumed
 
-    # -- target distribution (quant_calib.py:308-313)
+    # -- target distribution (quant_calib.py:228-232 / :308-313)
     def _raw_pred_softmax(self):
         dev = self._device()
         preds = []
         with torch.no_grad():
-            for inp, _ in self.calib_loader:
+            for inp in self._loader_batches():
                 preds.append(F.softmax(self.net(inp.to(dev)), dim=-1).detach())
-        return torch.cat(preds, dim=0)
+        raw = torch.cat(preds, dim=0)
+        if self.target_noise > 0:
+            gen = torch.Generator(device=raw.device).manual_seed(1234)
+            logits = raw.clamp_min(1e-30).log()
+            logits = logits + self.target_noise * torch.randn(logits.shape, generator=gen, device=logits.device)
+            raw = F.softmax(logits, dim=-1)
+        return raw
 
     def _fwd_bwd(self, raw_pred_softmax):
         """quant_calib.py:333-341: KL(self) backward in mini-batches of self.batch_size."""
         dev = self._device()
-        off = 0
-        for inp, target in self.calib_loader:
-            n = inp.shape[0]
-            for batch_st in range(0, n, self.batch_size):
-                self.net.zero_grad()
-                inp_ = inp[batch_st:batch_st + self.batch_size].to(dev)
-                pred = self.net(inp_)
-                tgt = raw_pred_softmax[off + batch_st:off + batch_st + self.batch_size]
-                loss = F.kl_div(F.log_softmax(pred, dim=-1), tgt, reduction="batchmean")
-                loss.backward()
-            off += n
+        for off, inp_ in self._mini_batches():
+            self.net.zero_grad()
+            inp_ = inp_.to(dev)
+            pred = self.net(inp_)
+            tgt = raw_pred_softmax[off:off + inp_.shape[0]]
+            loss = F.kl_div(F.log_softmax(pred, dim=-1), tgt, reduction="batchmean")
+            loss.backward()
 
-    def _hooks_for(self, module):
-        hooks = []
-        if isinstance(module, MinMaxQuantLinear):
-            hooks.append(module.register_forward_hook(linear_forward_hook))
-        if isinstance(module, MinMaxQuantMatMul):
-            hooks.append(module.register_forward_hook(matmul_forward_hook))
-        if hasattr(module, "metric"):
-            hooks.append(module.register_full_backward_hook(grad_hook))
-        return hooks
+    def _hooks_for(self, module, hessian_only=False):
+        want = hasattr(module, "metric") and (module.metric == "hessian" or not hessian_only)
+        return self._forward_hooks_for(module, want_grad=want)
+
+    # -- layer-wise sharding (only meaningful when sequential=False)
+    def _probe_shapes(self):
+        """Per-image input shapes of every wrapped module (one forward of one image, no grad)."""
+        shapes, hooks = {}, []
+
+        def rec(name):
+            def f(mod, inp, out):
+                if isinstance(mod, MinMaxQuantMatMul):
+                    shapes[name] = {"A": tuple(inp[0].shape[1:]), "B": tuple(inp[1].shape[1:]), "lead": int(inp[0].shape[0])}
+                elif isinstance(mod, MinMaxQuantConv2d):
+                    k = mod.kernel_size
+                    shapes[name] = {"conv_macs": float(out.shape[1] * out.shape[2] * out.shape[3] * mod.in_channels * k[0] * k[1])}
+                else:
+                    shapes[name] = {"x": tuple(inp[0].shape[1:]), "lead": int(inp[0].shape[0])}
+            return f
+        for n, m in self.wrapped_modules.items():
+            hooks.append(m.register_forward_hook(rec(n)))
+        first = next(iter(self._loader_batches()))
+        with torch.no_grad():
+            self.net(first[:1].to(self._device()))
+        for h in hooks:
+            h.remove()
+        # window attention folds windows into the batch dimension: lead = windows per image
+        for n, s in shapes.items():
+            lead = s.pop("lead", 1)
+            if "x" in s:
+                s["x"] = (lead,) + s["x"]
+            if "A" in s:
+                s["A"] = (lead,) + s["A"]
+        return shapes
 
     def _my_modules(self):
-        """Layer-wise sharding (only meaningful when sequential=False)."""
         names = list(self.wrapped_modules.keys())
         dist = self.distributed
         if dist is None or not dist.is_initialized() or dist.get_world_size() == 1 or self.sequential:
             return names, None
-        n_img = sum(inp.shape[0] for inp, _ in self.calib_loader)
-        costs = [module_cost(self.wrapped_modules[n], n_img) for n in names]
+        n_img = sum(inp.shape[0] for inp in self._loader_batches())
+        shapes = self._probe_shapes()
+        costs = [module_cost(self.wrapped_modules[n], n_img, shapes.get(n)) for n in names]
         owner = shard_modules(names, costs, dist.get_world_size())
         return [n for n in names if owner[n] == dist.get_rank()], owner
 
@@ -286,38 +431,44 @@ class HessianQuantCalibrator(QuantCalibrator):
         dist = self.distributed
         names = list(self.wrapped_modules.keys())
         mods = [self.wrapped_modules[n] for n in names]
-        width = result_width(mods)
+        width = result_width(mods) + 1          # last column: head count of MatMul modules (only their owner knows it)
         dev = self._device()
         mine = torch.zeros(len(names), width, dtype=torch.float32, device=dev)
-        heads = {}
         for i, n in enumerate(names):
             if owner[n] == dist.get_rank():
-                mine[i] = pack_result(mods[i], width).to(dev)
-        # head counts are only known to the owner of a MatMul module: ship them in the last column
-        meta = torch.zeros(len(names), dtype=torch.float32, device=dev)
-        for i, n in enumerate(names):
-            if owner[n] == dist.get_rank() and isinstance(mods[i], MinMaxQuantMatMul):
-                meta[i] = float(mods[i].n_G_B)
+                mine[i, :width - 1] = pack_result(mods[i], width - 1).to(dev)
+                if isinstance(mods[i], MinMaxQuantMatMul):
+                    mine[i, width - 1] = float(mods[i].n_G_B)
         gathered = [torch.zeros_like(mine) for _ in range(dist.get_world_size())]
-        gmeta = [torch.zeros_like(meta) for _ in range(dist.get_world_size())]
         dist.all_gather(gathered, mine)           # the one collective of the job
-        dist.all_gather(gmeta, meta)
         for i, n in enumerate(names):
             r = owner[n]
             if r != dist.get_rank():
-                h = int(gmeta[r][i].item()) if isinstance(mods[i], MinMaxQuantMatMul) else None
-                unpack_result(mods[i], gathered[r][i], heads=h)
+                h = int(gathered[r][i, width - 1].item()) if isinstance(mods[i], MinMaxQuantMatMul) else None
+                unpack_result(mods[i], gathered[r][i, :width - 1], heads=h)
+
+    def _snapshot(self, name, module):
+        if self.keep_captured is None:
+            return
+        if isinstance(module.raw_input, (list, tuple)):
+            d = {"A": module.raw_input[0], "B": module.raw_input[1]}
+        else:
+            d = {"x": module.raw_input}
+        d["y"] = module.raw_out
+        d["g"] = module.raw_grad
+        self.keep_captured[name] = {k: (v.detach().clone() if v is not None else None) for k, v in d.items()}
+
+    def _clock(self):
+        torch.cuda.synchronize(self._device()) if self._device().type == "cuda" else None
+        return time.perf_counter()
 
     def batching_quant_calib(self):
         """reference: quant_calib.py:300-378"""
+        t0 = self._clock()
         raw_pred_softmax = self._raw_pred_softmax()
-        if self.target_noise > 0:
-            gen = torch.Generator(device=raw_pred_softmax.device).manual_seed(1234)
-            logits = raw_pred_softmax.clamp_min(1e-30).log()
-            logits = logits + self.target_noise * torch.randn(logits.shape, generator=gen, device=logits.device)
-            raw_pred_softmax = F.softmax(logits, dim=-1)
         my_names, owner = self._my_modules()
         single_pass = (not self.sequential) and self.capture in ("auto", "single_pass")
+        t_capture = t_search = 0.0
         if single_pass:
             hooks = []
             for name in my_names:
@@ -325,29 +476,62 @@ class HessianQuantCalibrator(QuantCalibrator):
             self._fwd_bwd(raw_pred_softmax)
             for h in hooks:
                 h.remove()
+            self.net.zero_grad(set_to_none=True)
+            t1 = self._clock(); t_capture = t1 - t0
             for name in my_names:
                 module = self.wrapped_modules[name]
                 _cat_captured(module)
+                self._snapshot(name, module)
                 with torch.no_grad():
                     module.calibration_step2()
                 module.mode = "raw"
+            t2 = self._clock(); t_search = t2 - t1
         else:
+            t_capture = self._clock() - t0
             for name in my_names:
+                ta = self._clock()
                 module = self.wrapped_modules[name]
                 hooks = self._hooks_for(module)
                 self._fwd_bwd(raw_pred_softmax)
                 _cat_captured(module)
                 for h in hooks:
                     h.remove()
+                self._snapshot(name, module)
+                tb = self._clock(); t_capture += tb - ta
                 with torch.no_grad():
                     module.calibration_step2()
                 module.mode = "quant_forward" if self.sequential else "raw"
+                t_search += self._clock() - tb
+            t2 = self._clock()
         if owner is not None:
             self._gather(owner)
         for name, module in self.wrapped_modules.items():
             module.mode = "quant_forward"
         self.calibrated = True
+        t3 = self._clock()
+        self.timings = {"capture_s": t_capture, "search_s": t_search, "gather_s": t3 - t2, "total_s": t3 - t0,
+                        "modules_searched": len(my_names), "single_pass": bool(single_pass)}
 
-    # the reference's non-batching entry point maps onto the same machinery (quant_calib.py:216-298)
     def quant_calib(self):
-        return self.batching_quant_calib()
+        """reference: quant_calib.py:216-298 -- the non-batching driver: per module one forward+backward sweep, then
+        `calibration_step2(x)` / `(A, B)` with the captured input as argument (the Batching classes take none)."""
+        raw_pred_softmax = self._raw_pred_softmax()
+        dev = self._device()
+        for name, module in self.wrapped_modules.items():
+            hooks = self._hooks_for(module, hessian_only=True)
+            self._fwd_bwd(raw_pred_softmax)
+            _cat_captured(module)
+            for h in hooks:
+                h.remove()
+            self._snapshot(name, module)
+            with torch.no_grad():
+                if isinstance(module, (PTQSLBatchingQuantLinear, PTQSLBatchingQuantMatMul)) or getattr(module, "batching", False):
+                    module.calibration_step2()
+                elif isinstance(module, (MinMaxQuantLinear, MinMaxQuantConv2d)):
+                    module.calibration_step2(module.raw_input.to(dev))
+                elif isinstance(module, MinMaxQuantMatMul):
+                    module.calibration_step2(module.raw_input[0].to(dev), module.raw_input[1].to(dev))
+            module.mode = "quant_forward" if self.sequential else "raw"
+        for name, module in self.wrapped_modules.items():
+            module.mode = "quant_forward"
+        self.calibrated = True
