@@ -2,19 +2,25 @@
 """bench.py -- candidate-GEMMs/s of the PTQ4ViT scale-factor search on B200.
 
 A "step" = the full `calibration_step2` search of every wrapped Linear / MatMul of the workload
-(ViT-B/224, 32 synthetic images, W8A8, n_V=n_H=24 (qkv 72, head 1), n_a=1, eq_n=100, 3 rounds, hessian
+(default: ViT-B/224, 32 synthetic images, W8A8, n_V=n_H=24 (qkv 72, head 1), n_a=1, eq_n=100, 3 rounds, hessian
 metric = BASELINE.json configs[2] at one bit width) over tensors already resident in HBM.
-`value` = candidate-GEMM units of ALL ranks / max-over-ranks device time.  `e2e` = the same through the
-reference-facing call (`module.calibration_step2()`) with pinned HOST tensors, copies inside the timing.
+`value`   = candidate-GEMM units of ALL ranks / max-over-ranks device time.
+`e2e`     = the same through the reference-facing call (`module.calibration_step2()`) with pinned HOST tensors,
+            host<->device copies inside the timing.
+`calib_wallclock` = the public `HessianQuantCalibrator(...).batching_quant_calib()` (capture + search + gather), the
+            equivalent of what example/test_all.py:31-34 times.
+`reference_gpu` = the UNMODIFIED reference classes (baseline/_ref) on the same GPU, one layer per type, one round.
+`cpu_baseline` / `--impl reference` = the reference classes on the host cores (bounded sample, see below).
 
   python bench.py --gpus 1 --steps 3 --warmup 3
   torchrun ... bench.py --gpus N ...          (layer-sharded, one all_gather of the step sizes per step)
-  python bench.py --impl reference            (reference algorithm on the host cores, bounded sample)
+  python bench.py --impl reference            (reference on the host cores)
 """
 import argparse
 import ctypes
 import json
 import os
+import statistics
 import subprocess
 import sys
 import threading
@@ -22,10 +28,10 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("TQDM_DISABLE", "1")
 
 import torch  # noqa: E402
 
-METRIC = "candidate-GEMMs/s (scale-factor search, ViT-B/224 32-img W8A8)"
 UNIT = "cand-GEMM/s"
 
 
@@ -37,18 +43,28 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="vit_base_patch16_224")
     ap.add_argument("--images", type=int, default=32)
-    ap.add_argument("--blocks", type=int, default=24, help="n_V = n_H of the Linear layers (BASELINE: 24)")
+    ap.add_argument("--blocks", type=int, default=24, help="n_V = n_H of the Linear layers (BASELINE: 24; 1 = the reference's default)")
     ap.add_argument("--rounds", type=int, default=3)
     ap.add_argument("--bit", type=int, default=8)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--cpu-seconds", type=float, default=20.0)
+    ap.add_argument("--no-ref-gpu", action="store_true")
+    ap.add_argument("--no-wallclock", action="store_true")
+    ap.add_argument("--cpu-eq-n", type=int, default=20, help="candidates per search step of the CPU reference sample")
     return ap.parse_args()
+
+
+def metric_name(a):
+    return f"candidate-GEMMs/s (scale-factor search, {a.model} {a.images}-img W{a.bit}A{a.bit})"
 
 
 def workload_name(a):
     return (f"{a.model} {a.images} synthetic imgs W{a.bit}A{a.bit} n_V=n_H={a.blocks} (qkv x3, head 1) n_a=1 "
             f"eq_n=100 rounds={a.rounds} hessian")
+
+
+def is_default_workload(a):
+    return (a.model, a.images, a.blocks, a.rounds, a.bit) == ("vit_base_patch16_224", 32, 24, 3, 8)
 
 
 # ------------------------------------------------------------------ unit accounting
@@ -59,18 +75,16 @@ def units_of(module):
     return module.search_round * ((20 if module.sos else module.eq_n) + module.eq_n)
 
 
-def full_gemm_ops(module, shapes):
-    """2*M*K*O per Linear unit / 2*B*H*S1*S2*S3 per MatMul unit."""
-    from ptq4vit_b200.quant_layers.linear import MinMaxQuantLinear
-    if isinstance(module, MinMaxQuantLinear):
-        return 2.0 * shapes["rows"] * module.in_features * module.out_features
-    b, h, s1, s2, s3 = shapes["bmm"]
-    return 2.0 * b * h * s1 * s2 * s3
+def model_dims(a):
+    from ptq4vit_b200.utils.models import _ZOO
+    z = _ZOO[a.model]
+    tok = (z["img_size"] // z["patch"]) ** 2 + 1
+    return z["dim"], z["num_heads"], tok, z["depth"]
 
 
 # ------------------------------------------------------------------ workload construction
 def build_workload(a, device, rank, world):
-    """Synthetic ViT + one fwd/bwd capture sweep; returns {name: (module, tensors)} for THIS rank's shard."""
+    """Synthetic ViT + one fwd/bwd capture sweep; returns the net, the wrapped modules and THIS rank's shard."""
     import importlib
     from ptq4vit_b200.configs import PTQ4ViT as cfg
     from ptq4vit_b200.utils import quant_calib as Q
@@ -86,23 +100,24 @@ def build_workload(a, device, rank, world):
     wrapped = wrap_modules_in_net(net, cfg)
     gen = torch.Generator().manual_seed(3)               # mirrors calib_loader(seed=3), utils/datasets.py:88
     size = 384 if "384" in a.model else 224
-    images = torch.randn(a.images, 3, size, size, generator=gen)
+    images = torch.randn(a.images, 3, size, size, generator=gen).pin_memory()
     loader = [(images, None)]
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+    cal = Q.HessianQuantCalibrator(net, wrapped, loader, sequential=False, batch_size=4, target_noise=1.0, distributed=dist)
     names = list(wrapped.keys())
-    costs = [Q.module_cost(wrapped[n], a.images) for n in names]
-    owner = Q.shard_modules(names, costs, world)
-    mine = [n for n in names if owner[n] == rank]
-    cal = Q.HessianQuantCalibrator(net, wrapped, loader, sequential=False, batch_size=4, target_noise=1.0)
+    mine, owner = cal._my_modules()
+    if owner is None:
+        owner = {n: 0 for n in names}
     raw = cal._raw_pred_softmax()
-    g = torch.Generator(device=raw.device).manual_seed(1234)
-    logits = raw.clamp_min(1e-30).log() + torch.randn(raw.shape, generator=g, device=raw.device)
-    raw = torch.softmax(logits, dim=-1)
     hooks = []
     for n in mine:
         hooks += cal._hooks_for(wrapped[n])
     cal._fwd_bwd(raw)
     for h in hooks:
         h.remove()
+    net.zero_grad(set_to_none=True)
     work = {}
     for n in mine:
         m = wrapped[n]
@@ -113,9 +128,8 @@ def build_workload(a, device, rank, world):
             t = dict(x=m.raw_input.contiguous(), y=m.raw_out.contiguous(), g=m.raw_grad.contiguous())
         m.raw_input = m.raw_out = m.raw_grad = None
         work[n] = (m, t)
-    del net, cal
     torch.cuda.empty_cache()
-    return wrapped, work, owner, names
+    return net, wrapped, work, owner, names, cal
 
 
 def run_module(m, t):
@@ -126,14 +140,6 @@ def run_module(m, t):
         m.raw_input, m.raw_out, m.raw_grad = [t["A"], t["B"]], t["y"], t["g"]
     with torch.no_grad():
         m.calibration_step2()
-
-
-def gather_results(wrapped, owner, names, dist, device):
-    from ptq4vit_b200.utils import quant_calib as Q
-    if dist is None:
-        return
-    cal = Q.HessianQuantCalibrator(torch.nn.Linear(1, 1).to(device), wrapped, [], distributed=dist)
-    cal._gather(owner)
 
 
 class ClockSampler:
@@ -173,80 +179,149 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ------------------------------------------------------------------ CPU reference arm (oracle port)
-def cpu_reference_rate(a, seconds_budget):
-    """Time the reference algorithm (oracle port: fp32 fake-quant + full GEMM + Hessian-weighted error per
-    candidate) on the host cores, one layer of each type at the workload's sizes, a few candidates each,
-    and extrapolate: total_time = sum(units_type / rate_type)."""
-    from oracle import ptq_oracle as O
-    torch.set_num_threads(os.cpu_count() or 1)
-    dims = {"vit_base": (768, 12), "deit_base": (768, 12), "vit_small": (384, 6), "deit_small": (384, 6), "vit_tiny": (192, 3)}
-    D, H = next(v for k, v in dims.items() if a.model.startswith(k))
-    tok = (384 // 16) ** 2 + 1 if "384" in a.model else 197
-    depth = 12
+# ------------------------------------------------------------------ the reference, timed (CPU arm and GPU comparator)
+def layer_types(a):
+    """One layer of every type of the workload: name -> (kind, shape spec, module kwargs, count in the model, units per layer)."""
+    D, H, tok, depth = model_dims(a)
     nb = a.blocks
-    lin_types = {"qkv": (D, 3 * D, 3 * nb, False), "proj": (D, D, nb, False), "fc1": (D, 4 * D, nb, False), "fc2": (4 * D, D, nb, True)}
-    counts, rates, detail = {}, {}, {}
-    per_type_budget = seconds_budget / 6.0
-    for name, (K, Oo, nV, gelu) in lin_types.items():
-        x, W, b, y, g = O.make_linear_fixture(1, a.images, tok, K, Oo, post_gelu=gelu)
-        sp = O.LinearSpec(K, Oo, n_V=nV, n_H=nb, n_a=1, w_bit=a.bit, a_bit=a.bit, eq_n=2, search_round=1, post_gelu=gelu)
-        w_int, a_int = O.linear_initial_intervals(sp, W, x)
-        f = O.candidate_factors(0.01, 1.2, 100)[:3]
-        wc = f.view(-1, 1, 1, 1, 1) * w_int.unsqueeze(0); ac = f.view(1, 1, -1) * a_int.unsqueeze(-1)
-        t0 = time.time(); n = 0
-        while time.time() - t0 < per_type_budget or n == 0:
-            O.linear_search_w(sp, W, b, x, y, g, w_int, a_int, wc, chunk=2, h_list=[0]); n += 2
-            O.linear_search_a(sp, W, b, x, y, g, w_int, a_int, ac); n += 2
-        dt = time.time() - t0
-        rates[name] = n / dt
-        counts[name] = depth * a.rounds * (nb + 1) * 100
-        detail[name] = {"cands": n, "s": round(dt, 2)}
-    for name, (sos, S2, S3) in {"matmul1": (False, D // H, tok), "matmul2": (True, tok, D // H)}.items():
-        A, B, Y, G = O.make_matmul_fixture(2, a.images, H, tok, S2, S3, softmax_A=sos)
-        sp = O.MatMulSpec(A_bit=a.bit, B_bit=a.bit, eq_n=2, search_round=1, sos=sos)
-        A_int, B_int = O.matmul_initial_intervals(sp, A, B)
-        fB = O.candidate_factors(0.01, 1.2, 100)[:3].view(-1, 1, 1, 1, 1, 1, 1, 1) * B_int.unsqueeze(0)
-        split = torch.tensor(0.5); Ai = split / (sp.A_qmax - 1) if sos else A_int
-        t0 = time.time(); n = 0
-        while time.time() - t0 < per_type_budget or n == 0:
-            O.matmul_search_B(sp, A, B, Y, G, Ai, B_int, fB, split if sos else None); n += 2
-        dt = time.time() - t0
-        rates[name] = n / dt
-        counts[name] = depth * a.rounds * ((20 if sos else 100) + 100)
-        detail[name] = {"cands": n, "s": round(dt, 2)}
-    total_units = sum(counts.values())
-    total_time = sum(counts[k] / rates[k] for k in counts)
-    return total_units / total_time, {"per_type_rate": {k: round(v, 3) for k, v in rates.items()}, "timed": detail,
-                                      "extrapolated_full_job_s": round(total_time, 1)}
+    lin = dict(n_H=nb, n_a=1, w_bit=a.bit, a_bit=a.bit)
+    per_lin = a.rounds * (nb + 1) * 100
+    types = {
+        "qkv": ("linear", (D, 3 * D, False, tok), dict(lin, n_V=3 * nb), depth, per_lin),
+        "proj": ("linear", (D, D, False, tok), dict(lin, n_V=nb), depth, per_lin),
+        "fc1": ("linear", (D, 4 * D, False, tok), dict(lin, n_V=nb), depth, per_lin),
+        "fc2": ("linear", (4 * D, D, True, tok), dict(lin, n_V=nb), depth, per_lin),
+        "head": ("linear", (D, 1000, False, 0), dict(lin, n_V=1), 1, per_lin),
+        "matmul1": ("matmul", (H, tok, D // H, tok, False), dict(A_bit=a.bit, B_bit=a.bit), depth, a.rounds * 200),
+        "matmul2": ("matmul", (H, tok, tok, D // H, True), dict(A_bit=a.bit, B_bit=a.bit), depth, a.rounds * 120),
+    }
+    return types
+
+
+def reference_rates(a, on_gpu, eq_n, only=None):
+    """Times the reference classes (oracle/ref_harness -> baseline/_ref; falls back to the oracle port) on one seeded
+    synthetic layer of every type at the workload's sizes.  GPU: the whole calibration_step2() of one round, eq_n=100,
+    the reference's own H2D copies included.  CPU: eq_n candidates per search step, the weight search of a Linear layer
+    interrupted after one column block (+ one activation step).  Returns {type: (seconds, units)} and the kind."""
+    from oracle import ptq_oracle as O
+    from oracle import ref_harness as RH
+    kind = "reference" if RH.available() else "port"
+    out = {}
+    for i, (name, (k, shape, mod, count, per_layer)) in enumerate(layer_types(a).items()):
+        if only and name not in only:
+            continue
+        if k == "linear":
+            K, Oo, gelu, tok = shape
+            x, W, b, y, g = O.make_linear_fixture(40 + i, a.images, tok, K, Oo, post_gelu=gelu)
+            if kind == "reference":
+                out[name] = RH.time_linear(x, W, b, y, g, gelu, eq_n, w_blocks=None if on_gpu else 1, search_round=1, **mod)
+            else:
+                out[name] = _port_linear(O, x, W, b, y, g, gelu, eq_n, on_gpu, mod)
+        else:
+            H, S1, S2, S3, sos = shape
+            A, B, Y, G = O.make_matmul_fixture(60 + i, a.images, H, S1, S2, S3, softmax_A=sos)
+            if kind == "reference":
+                out[name] = RH.time_matmul(A, B, Y, G, sos, eq_n, search_round=1, **mod)
+            else:
+                out[name] = _port_matmul(O, A, B, Y, G, sos, eq_n, on_gpu, mod)
+    return out, kind
+
+
+def _port_linear(O, x, W, b, y, g, gelu, eq_n, on_gpu, mod):
+    dev = "cuda" if on_gpu else "cpu"
+    sp = O.LinearSpec(W.shape[1], W.shape[0], n_V=mod["n_V"], n_H=mod["n_H"], n_a=1, w_bit=mod["w_bit"], a_bit=mod["a_bit"],
+                      eq_n=eq_n, search_round=1, post_gelu=gelu)
+    x, W, b, y, g = [t.to(dev) for t in (x, W, b, y, g)]
+    t0 = time.perf_counter()
+    w_int, a_int = O.linear_initial_intervals(sp, W, x)
+    f = O.candidate_factors(0.01, 1.2, eq_n).to(dev)
+    wc = f.view(-1, 1, 1, 1, 1) * w_int.unsqueeze(0); ac = f.view(1, 1, -1) * a_int.unsqueeze(-1)
+    hl = None if on_gpu else [0]
+    O.linear_search_w(sp, W, b, x, y, g, w_int, a_int, wc, h_list=hl)
+    O.linear_search_a(sp, W, b, x, y, g, w_int, a_int, ac)
+    if on_gpu:
+        torch.cuda.synchronize()
+    return time.perf_counter() - t0, ((sp.n_H if on_gpu else 1) + 1) * eq_n
+
+
+def _port_matmul(O, A, B, Y, G, sos, eq_n, on_gpu, mod):
+    dev = "cuda" if on_gpu else "cpu"
+    sp = O.MatMulSpec(A_bit=mod["A_bit"], B_bit=mod["B_bit"], eq_n=eq_n, search_round=1, sos=sos)
+    A, B, Y, G = [t.to(dev) for t in (A, B, Y, G)]
+    t0 = time.perf_counter()
+    O.matmul_calibrate(sp, A, B, Y, G)
+    if on_gpu:
+        torch.cuda.synchronize()
+    return time.perf_counter() - t0, (20 if sos else eq_n) + eq_n
+
+
+def extrapolate(a, samples):
+    """samples {type: (seconds, units)} -> (cand-GEMM/s of the whole job, job seconds, per-type rate)."""
+    types = layer_types(a)
+    total_units = total_s = 0.0
+    rates = {}
+    for name, (sec, units) in samples.items():
+        k, shape, mod, count, per_layer = types[name]
+        rates[name] = units / sec
+        total_units += count * per_layer
+        total_s += count * per_layer / rates[name]
+    return total_units / total_s, total_s, rates
+
+
+def physical_cores():
+    try:
+        import psutil
+        n = psutil.cpu_count(logical=False)
+        if n:
+            return min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+def reference_cpu_main(a):
+    """`--impl reference`: the reference's own classes on the host cores (harness-only `.cuda()` no-op shim so that
+    the hard-coded device moves of the Batching classes stay on the CPU)."""
+    from oracle import ref_harness as RH
+    t_start = time.time()
+    cores = physical_cores()
+    torch.set_num_threads(cores)
+    RH.cpu_shim()
+    if hasattr(torch.cuda, "synchronize"):
+        torch.cuda.is_available = lambda: False
+    vals, per_step = [], []
+    for i in range(a.warmup + a.steps):
+        eq_n = 4 if i < a.warmup else a.cpu_eq_n           # warm-up: thread pools, allocator, first-touch of the fixtures
+        samples, kind = reference_rates(a, on_gpu=False, eq_n=eq_n)
+        v, job_s, rates = extrapolate(a, samples)
+        if i >= a.warmup:
+            vals.append(v)
+            per_step.append({"value": round(v, 3), "job_s": round(job_s, 1), "sample_s": round(sum(s for s, _ in samples.values()), 2),
+                             "rates": {k: round(r, 3) for k, r in rates.items()}})
+    value = statistics.median(vals)
+    sample = (f"{'unmodified reference classes (baseline/_ref)' if kind == 'reference' else 'oracle port'} on {cores} threads "
+              f"(physical cores, torch.set_num_threads): one seeded synthetic layer per type (qkv, proj, fc1, fc2, head, matmul1, matmul2) at "
+              f"the workload's sizes; Linear: one column block of the weight search + the activation search, {a.cpu_eq_n} candidates "
+              f"each; MatMul: calibration_step2 with eq_n={a.cpu_eq_n}, one round; extrapolated by unit counts to the whole job; "
+              f"median of {a.steps} step(s), spread {min(vals):.3f}..{max(vals):.3f}")
+    out = {"impl": "reference", "metric": metric_name(a), "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+           "warmup": a.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic", "config": {"workload": workload_name(a)},
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+                            "spread": [min(vals), max(vals)], "per_step": per_step},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "wall_s": round(time.time() - t_start, 1)}
+    print(json.dumps(out))
 
 
 def main():
     a = parse()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    cores = os.cpu_count() or 1
 
     if a.impl == "reference":
-        if rank != 0:
-            return
-        t0 = time.time()
-        vals = []
-        per = max(5.0, min(a.cpu_seconds, 60.0))
-        for i in range(a.warmup + a.steps):
-            v, info = cpu_reference_rate(a, per / max(1, a.warmup + a.steps) * 3)
-            if i >= a.warmup:
-                vals.append(v)
-        value = sum(vals) / len(vals)
-        out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
-               "warmup": a.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-               "dtype": "f32", "data": "synthetic", "config": {"workload": workload_name(a)},
-               "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": "oracle port of the reference search, one layer per type (qkv, proj, fc1, fc2, matmul1, matmul2) at full "
-                                          "size, a few candidates each, extrapolated by unit counts; " + json.dumps(info)},
-               "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-               "wall_s": round(time.time() - t0, 1)}
-        print(json.dumps(out))
+        if rank == 0:
+            reference_cpu_main(a)
         return
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback for the product path)"
@@ -260,17 +335,21 @@ def main():
     from ptq4vit_b200 import _lib
     lib = _lib.lib()
 
-    wrapped, work, owner, names = build_workload(a, device, rank, world)
+    net, wrapped, work, owner, names, cal = build_workload(a, device, rank, world)
     my_units = sum(units_of(m) for m, _ in work.values())
     units_t = torch.tensor([float(my_units)], device=device)
     if dist:
         dist.all_reduce(units_t)
     total_units = float(units_t.item())
 
+    def gather():
+        if dist:
+            cal._gather(owner)
+
     def step():
         for m, t in work.values():
             run_module(m, t)
-        gather_results(wrapped, owner, names, dist, device)
+        gather()
 
     def sync_all():
         torch.cuda.synchronize()
@@ -281,7 +360,7 @@ def main():
     for _ in range(a.warmup):
         step()
     sync_all()
-    sampler = ClockSampler(local);
+    sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     lib.p4v_profile_enable(1)
@@ -295,8 +374,8 @@ def main():
     sync_all()
     ms = e0.elapsed_time(e1)
     lib.p4v_profile_enable(0)
-    sweep_ms, sweep_n, sweep_ops = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double()
-    lib.p4v_profile_collect(ctypes.byref(sweep_ms), ctypes.byref(sweep_n), ctypes.byref(sweep_ops))
+    prof = (ctypes.c_double * 12)()
+    lib.p4v_profile_collect_kinds(prof, 12)
     launches = _lib.launch_count() - n0
     clocks = sampler.stop() if rank == 0 else None
     tmax = torch.tensor([ms], device=device)
@@ -304,6 +383,29 @@ def main():
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms = float(tmax.item())
     value = total_units * a.steps / (ms / 1e3)
+
+    # ---- the public calibrator: capture + search + gather (what example/test_all.py:31-34 times)
+    wallclock = None
+    if not a.no_wallclock:
+        runs = []
+        for _ in range(2):
+            for m in wrapped.values():
+                if hasattr(m, "calibrated"):
+                    del m.calibrated
+                m.mode = "raw"
+            sync_all()
+            cal.batching_quant_calib()
+            t = cal.timings
+            tt = torch.tensor([t["total_s"], t["capture_s"], t["search_s"], t["gather_s"]], device=device, dtype=torch.float64)
+            if dist:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            runs.append([float(v) for v in tt.tolist()])
+        total_s, capture_s, search_s, gather_s = runs[-1]
+        wallclock = {"total_s": total_s, "capture_s": capture_s, "search_s": search_s, "gather_s": gather_s,
+                     "first_run_total_s": runs[0][0],
+                     "what": "HessianQuantCalibrator(net, wrapped, loader, sequential=False, batch_size=4).batching_quant_calib(): "
+                             "KL target pass, one forward+backward sweep with hooks on this rank's modules, search, all_gather; "
+                             "max over ranks; images start in pinned host memory"}
 
     # ---- end to end through the public call with HOST (pinned) tensors
     e2e = None
@@ -313,10 +415,8 @@ def main():
         for n, (m, t) in work.items():
             host[n] = {k: v.cpu().pin_memory() for k, v in t.items()}
             h2d += sum(v.numel() * 4 for v in t.values())
-        saved = {n: t for n, (m, t) in work.items()}
         for n in work:
             work[n] = (work[n][0], None)
-        del saved
         torch.cuda.empty_cache()
         d2h = 0
 
@@ -327,7 +427,7 @@ def main():
             # pinned host tensors -> (copy stream, one module ahead) -> search -> step sizes back to pinned host memory
             nonlocal d2h
             _, d2h = search_from_host(items, device)
-            gather_results(wrapped, owner, names, dist, device)
+            gather()
 
         e2e_step()
         sync_all()
@@ -350,47 +450,99 @@ def main():
         e2e = {"value": total_units * k_e2e / (float(et.item()) / 1e3), "unit": UNIT,
                "h2d_bytes_per_step": int(hb[0].item()), "d2h_bytes_per_step": int(hb[1].item()), "steps": k_e2e,
                "ms_per_step": float(et.item()) / k_e2e, "clocks": e2e_clocks}
+        del host, items
 
     if rank != 0:
         if dist:
             dist.destroy_process_group()
         return
 
+    # ---- roofline: per launch kind against its own peak
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     bf16_peak = peaks.get("bf16_tflops_sustained") or 1400.0
-    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16, measured)" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
-    achieved = sweep_ops.value / (sweep_ms.value / 1e3) / 1e12 if sweep_ms.value > 0 else 0.0
-    roofline = {"bound": "tensor", "achieved": achieved, "peak": bf16_peak, "unit": "TFLOP/s", "frac": achieved / bf16_peak,
-                # DRAM bytes (read+write) of the dominant sweep launch from profiles/r01_sweep_xstep_qkv.ncu-rep (ncu --set full):
-                # the ViT-B qkv activation step, 4.90 ms, 2.26 TFLOP executed; algorithmic bytes of that launch =
-                # candidate planes of X 968 MB + y,g once 116 MB + weight image 3.5 MB + partial scores 11.5 MB = 1.10 GB
-                "traffic": 1230711296, "traffic_of": "qkv activation-step launch (algorithmic 1.10e9 B)", "kernel": "sweep_tc_kernel", "launches": int(sweep_n.value),
-                "avg_launch_ms": sweep_ms.value / max(1, sweep_n.value), "share_of_step": sweep_ms.value / ms,
-                "note": "achieved = EXECUTED tensor-core ops (slab-incremental: only the K segment a candidate changes is multiplied) / "
-                        "summed CUDA-event time of the sweep launches of this rank; peak = " + peak_src +
-                        "; slab sweeps only (the Gram GEMM of the weight steps is a separate kernel: 1.53 PFLOP/s executed, "
-                        "profiles/r01_final_ncu_summary.csv); the sweep is bound by the per-accumulator hand-over (fp32 epilogue, "
-                        "TMEM load latency, single-warp issue loop) at 32-wide slabs, see DESIGN.md 4.1"}
-    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+    bf16_burst = peaks.get("bf16_tflops") or 1700.0
+    peak_src = "MEASURED_PEAKS.json (cuBLAS bf16: sustained inside a long step, burst for a launch alone)" if peaks else \
+        "fallback 1.4 / 1.7 PFLOP/s (B200_PROFILING.md)"
+    kinds = ["sweep_bf16", "sweep_int8", "gram_gemm"]
+    kernels = {"sweep_bf16": "sweep_tc_kernel<f32 accumulators>", "sweep_int8": "sweep_tc_kernel<s32 accumulators>", "gram_gemm": "gram_gemm_kernel"}
+    by_kind = {}
+    for i, k in enumerate(kinds):
+        t_ms, ops, n = prof[i], prof[3 + i], int(prof[6 + i])
+        if n == 0:
+            continue
+        pk = bf16_peak * (2.0 if k == "sweep_int8" else 1.0)
+        ach = ops / (t_ms / 1e3) / 1e12
+        by_kind[k] = {"kernel": kernels[k], "ms": t_ms, "launches": n, "avg_launch_ms": t_ms / n, "share_of_step": t_ms / ms,
+                      "achieved": ach, "peak": pk, "frac": ach / pk, "unit": "TOP/s" if k == "sweep_int8" else "TFLOP/s"}
+    dom = max(by_kind, key=lambda k: by_kind[k]["ms"])
+    top_kind = kinds[int(prof[11])]
+    top_peak = bf16_burst * (2.0 if top_kind == "sweep_int8" else 1.0)
+    top_ach = prof[10] / (prof[9] / 1e3) / 1e12 if prof[9] > 0 else 0.0
+    # DRAM bytes (read + write) of the longest launch from this round's `ncu --set full` capture (profiles/): a measured
+    # constant of the DEFAULT workload, omitted for any other arguments
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if is_default_workload(a):
+            traffic = tr.get("dominant_launch_dram_bytes")
+    except Exception:
+        tr = {}
+    roofline = {"bound": "tensor", "kernel": by_kind[dom]["kernel"], "achieved": by_kind[dom]["achieved"], "peak": by_kind[dom]["peak"],
+                "unit": by_kind[dom]["unit"], "frac": by_kind[dom]["frac"], "traffic": traffic,
+                "traffic_note": tr.get("note") if traffic is not None else "ncu DRAM bytes are recorded for the default workload only",
+                "by_kind": by_kind,
+                "longest_launch": {"kind": top_kind, "ms": prof[9], "achieved": top_ach, "peak": top_peak, "frac": top_ach / top_peak,
+                                   "peak_is": "burst (a launch timed alone)"},
+                "note": "achieved = EXECUTED tensor-core operations (slab-incremental search: only the K segment a candidate changes is "
+                        "multiplied; Gram GEMM: three bf16 term products) / CUDA-event time of the launches of that kind on this rank; "
+                        "peak = " + peak_src + "; int8 launches are held against 2x the measured bf16 rate (stated, not measured: "
+                        "MEASURED_PEAKS.json has no int8 figure)"}
+    out = {"metric": metric_name(a), "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
            "dtype": "int8/bf16-int operands, s32/f32 accumulate, f32 error", "data": "synthetic",
            "config": {"workload": workload_name(a), "parallelism": f"layer-sharded x{world}", "units_per_step": total_units,
-                      "l2": "inputs (9.5 GB of staged tensors per step) are larger than L2; no explicit flush"},
+                      "l2": "inputs (the staged tensors of a step, 9.5 GB for the default workload) are larger than L2; no explicit flush"},
            "calib_search_wallclock_s": ms / a.steps / 1e3,
            "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline}
+    if wallclock:
+        out["calib_wallclock_s"] = wallclock["total_s"]
+        out["calib_wallclock"] = wallclock
     if e2e:
         out["e2e"] = e2e
-    if not a.no_cpu:
-        v, info = cpu_reference_rate(a, a.cpu_seconds)
-        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                               "sample": "oracle port, one layer per type at full size, a few candidates each, extrapolated by unit counts; " + json.dumps(info)}
-    print(json.dumps(out))
     if dist:
         dist.destroy_process_group()
+    del work
+    torch.cuda.empty_cache()
+    if world == 1 and not a.no_ref_gpu:
+        try:
+            samples, kind = reference_rates(a, on_gpu=True, eq_n=100)
+            samples, kind = reference_rates(a, on_gpu=True, eq_n=100)          # second pass: warm allocator / cuBLAS handles
+            v, job_s, rates = extrapolate(a, samples)
+            out["reference_gpu"] = {"value": v, "unit": UNIT, "kind": kind, "extrapolated_full_job_s": job_s,
+                                    "per_type_units_per_s": {k: round(r, 1) for k, r in rates.items()},
+                                    "per_type_s_one_round": {k: round(s, 3) for k, (s, _) in samples.items()},
+                                    "sample": "the reference's own eager GPU path (calibration_step2 of the unmodified classes, CPU-resident "
+                                              "captured tensors as its hooks leave them) on this GPU: one seeded synthetic layer per type at the "
+                                              "workload's sizes, one search round, eq_n=100; extrapolated by unit counts",
+                                    "speedup_device": value / v, "speedup_e2e": (e2e["value"] / v) if e2e else None}
+        except Exception as exc:   # the comparator must never take the bench line down
+            out["reference_gpu"] = {"unavailable": repr(exc)[:200]}
+    if world == 1 and not a.no_cpu:
+        try:
+            cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                   "--model", a.model, "--images", str(a.images), "--blocks", str(a.blocks), "--rounds", str(a.rounds),
+                   "--bit", str(a.bit), "--cpu-eq-n", str(a.cpu_eq_n)]
+            env = dict(os.environ); env["CUDA_VISIBLE_DEVICES"] = ""
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+            line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
+            out["cpu_baseline"] = json.loads(line)["cpu_baseline"]
+        except Exception as exc:
+            out["cpu_baseline"] = {"unavailable": repr(exc)[:200]}
+    print(json.dumps(out))
 
 
 if __name__ == "__main__":

@@ -126,6 +126,10 @@ P4V_API long long p4v_launch_count(void);
  * executed, then clears the record. */
 P4V_API int p4v_profile_enable(int on);
 P4V_API int p4v_profile_collect(double* sweep_ms, long long* sweep_launches, double* executed_ops);
+/* The same record split by launch kind: out[0..2] = device ms of the bf16 slab sweeps, the int8 slab sweeps and the Gram
+ * GEMMs, out[3..5] = tensor-core operations they executed, out[6..8] = launches, out[9..11] = the longest single launch
+ * (ms, operations, kind).  n must be >= 12. */
+P4V_API int p4v_profile_collect_kinds(double* out, int n);
 /* Device self-test of the quantiser's division shortcut: evaluates round(v / delta) for n pseudo-random (v, delta)
  * pairs (plus pairs placed on and next to rounding ties) both with IEEE division, as the reference does
  * (quant_layers/linear.py:99-103 `(x / interval).round_()`), and with the reciprocal-based sequence the operand

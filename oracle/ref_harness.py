@@ -297,3 +297,83 @@ def collect_intervals(wrapped):
             d[key] = torch.as_tensor(v).detach().float().cpu().reshape(-1).clone()
         out[name] = d
     return out
+
+
+# ---------------------------------------------------------------- timing the reference (bench.py's reference legs)
+class _StopSearch(Exception):
+    pass
+
+
+@contextlib.contextmanager
+def _stop_after_argmax(n):
+    """Interrupt the reference's greedy loop after its n-th argmax (= after n search steps)."""
+    orig = torch.Tensor.argmax
+    seen = [0]
+
+    def spy(self, *a, **k):
+        r = orig(self, *a, **k)
+        seen[0] += 1
+        if seen[0] >= n:
+            raise _StopSearch()
+        return r
+    torch.Tensor.argmax = spy
+    try:
+        yield
+    finally:
+        torch.Tensor.argmax = orig
+
+
+def _sync():
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+
+
+def time_linear(x, W, b, y, g, post_gelu, eq_n, w_blocks=None, **mod):
+    """Seconds and candidate-GEMM units of the reference's Linear search on the given tensors (CPU tensors in, as its
+    hooks leave them).  w_blocks=None: the whole `calibration_step2()` (search_round rounds); w_blocks=k: the unmodified
+    `_search_best_w_interval` interrupted after k column blocks plus one full `_search_best_a_interval`
+    (bounded sample for the CPU arm; the per-candidate work is the same in every column block)."""
+    import time
+    R = load()
+    cls = R.linear.PostGeluPTQSLBatchingQuantLinear if post_gelu else R.linear.PTQSLBatchingQuantLinear
+    kw = dict(COMMON); kw.update(mod); kw["eq_n"] = eq_n
+    m = cls(W.shape[1], W.shape[0], bias=b is not None, **kw)
+    m.weight.data = W.clone()
+    if b is not None:
+        m.bias.data = b.clone()
+    m.to(_dev())
+    m.raw_input, m.raw_out, m.raw_grad = x, y, g
+    _sync(); t0 = time.perf_counter()
+    with torch.no_grad():
+        if w_blocks is None:
+            m.calibration_step2()
+            units = m.search_round * (m.n_H + m.n_a) * eq_n
+        else:
+            m._initialize_calib_parameters()
+            m._initialize_intervals()
+            f = torch.tensor([m.eq_alpha + i * (m.eq_beta - m.eq_alpha) / m.eq_n for i in range(m.eq_n + 1)]).to(m.w_interval.device)
+            wc = f.view(-1, 1, 1, 1, 1) * m.w_interval.unsqueeze(0)          # linear.py:544
+            ac = f.view(1, 1, -1) * m.a_interval.unsqueeze(-1)               # linear.py:545
+            try:
+                with _stop_after_argmax(w_blocks):
+                    m._search_best_w_interval(wc)
+            except _StopSearch:
+                pass
+            m._search_best_a_interval(ac)
+            units = (min(w_blocks, m.n_H) + m.n_a) * eq_n
+    _sync()
+    return time.perf_counter() - t0, units
+
+
+def time_matmul(A, B, Y, G, sos, eq_n, **mod):
+    import time
+    R = load()
+    cls = R.matmul.SoSPTQSLBatchingQuantMatMul if sos else R.matmul.PTQSLBatchingQuantMatMul
+    kw = dict(COMMON); kw.update(mod); kw["eq_n"] = eq_n
+    m = cls(**kw)
+    m.raw_input, m.raw_out, m.raw_grad = [A, B], Y, G
+    _sync(); t0 = time.perf_counter()
+    with torch.no_grad():
+        m.calibration_step2()
+    _sync()
+    return time.perf_counter() - t0, m.search_round * ((20 if sos else eq_n) + eq_n)

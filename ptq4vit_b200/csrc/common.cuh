@@ -73,6 +73,7 @@ struct SweepParams {
   int out_residual;         // with out: write y - bias - sum(scale*acc) instead (the current residual e)
   int order;                // 0: tile_m fastest, 1: tile_n fastest
   int is_int8;
+  int acc_elem_bound;       // max |row element| * |column element| of the integer operands (0: 128*128); bounds the s32 accumulators
   // shared-memory plan, filled by the launcher
   unsigned int stage_r_bytes, stage_c_bytes, n_stages, resident_bytes, resident_bufs, cres_bytes;
   long long* trace;         // debug: clock64 timeline of CTA 0 ([3 roles][512 events][4]) or null

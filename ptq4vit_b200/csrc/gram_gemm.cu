@@ -19,6 +19,9 @@
 
 void p4v_count_launch();
 int p4v_num_sms();
+bool p4v_prof_on();
+void p4v_prof_begin(cudaStream_t st, cudaEvent_t* e0);
+void p4v_prof_end(cudaStream_t st, cudaEvent_t e0, int kind, double ops);
 
 namespace {
 
@@ -227,7 +230,11 @@ int p4v_gram_gemm(const GramGemmArgs& a, cudaStream_t st) {
   const int grid = tiles < p4v_num_sms() ? tiles : p4v_num_sms();
   const size_t smem = (size_t)kStages * kStageBytes + sizeof(Ctl) + 256;
   P4V_CUDA_OK(cudaFuncSetAttribute(gram_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaEvent_t e0 = nullptr;
+  if (p4v_prof_on()) p4v_prof_begin(st, &e0);
   gram_gemm_kernel<<<grid, kThreads, smem, st>>>(a); p4v_count_launch();
+  // three bf16 term products per (output channel, pair, token): 128x256 tiles over term_bytes/2 tokens
+  if (p4v_prof_on()) p4v_prof_end(st, e0, 2, 3.0 * 2.0 * 128.0 * 256.0 * (double)tiles * (double)(a.term_bytes / 2));
   P4V_CUDA_OK(cudaGetLastError());
   return 0;
 }

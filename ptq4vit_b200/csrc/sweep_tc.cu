@@ -226,9 +226,15 @@ __device__ __forceinline__ bool next_frag(const SweepParams& P, Sched& s, Frag& 
   return true;
 }
 
-template <bool kInt8>
+// Accumulator element -> float.  kAcc: 0 = fp32 accumulator (integer-valued bf16 operands), 1 = s32 accumulator through
+// the convert unit (I2F: a quarter of the FMA rate, any magnitude), 2 = s32 accumulator with |acc| < 2^22 (the launcher
+// checks the bound of every accumulator chain): 0x4B400000 + acc read as a float is 1.5*2^23 + acc exactly, so the
+// convert is one integer add and one float add, both on full-rate pipes.
+constexpr int kAccF32 = 0, kAccI2F = 1, kAccMagic = 2;
+template <int kAcc>
 __device__ __forceinline__ float acc_to_float(uint32_t a) {
-  if constexpr (kInt8) return __int2float_rn((int)a);
+  if constexpr (kAcc == kAccI2F) return __int2float_rn((int)a);
+  else if constexpr (kAcc == kAccMagic) return __uint_as_float(a + 0x4B400000u) - 12582912.f;
   else return __uint_as_float(a);
 }
 
@@ -237,20 +243,28 @@ typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pack2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
 __device__ __forceinline__ void unpack2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
+template <int kAcc>
+__device__ __forceinline__ f32x2 acc_pair(uint32_t a0, uint32_t a1) {
+  if constexpr (kAcc == kAccMagic)
+    return add2(pack2(__uint_as_float(a0 + 0x4B400000u), __uint_as_float(a1 + 0x4B400000u)), pack2(-12582912.f, -12582912.f));
+  else return pack2(acc_to_float<kAcc>(a0), acc_to_float<kAcc>(a1));
+}
 
 // A quarter of this thread's 64 accumulator columns (16 columns = one scale / score group, already in registers)
 // against the running residual.
 //   kScore == false:  r -= s * acc                        (fixed segments / non-final candidate segments)
 //   kScore == true :  p = sum (g * (r - s*acc))^2          (final candidate segment; r is not modified)
-template <bool kInt8, bool kScore, bool kPacked, int OFF>
+template <int kAcc, bool kScore, bool kPacked, int OFF>
 __device__ __forceinline__ void consume16(const uint32_t (&a)[16], float (&r)[64], const float (&g)[64], const float s, float& p) {
   if constexpr (kPacked) {
     f32x2 q0 = 0ull, q1 = 0ull;
     const f32x2 ns = pack2(-s, -s);
 #pragma unroll
     for (int j = 0; j < 16; j += 2) {
-      const f32x2 f = pack2(acc_to_float<kInt8>(a[j]), acc_to_float<kInt8>(a[j + 1]));
+      const f32x2 f = acc_pair<kAcc>(a[j], a[j + 1]);
       const f32x2 d = fma2(ns, f, pack2(r[OFF + j], r[OFF + j + 1]));
       if constexpr (kScore) {
         const f32x2 w = mul2(pack2(g[OFF + j], g[OFF + j + 1]), d);
@@ -264,7 +278,7 @@ __device__ __forceinline__ void consume16(const uint32_t (&a)[16], float (&r)[64
     float q0 = 0.f, q1 = 0.f;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      const float d = fmaf(-s, acc_to_float<kInt8>(a[j]), r[OFF + j]);
+      const float d = fmaf(-s, acc_to_float<kAcc>(a[j]), r[OFF + j]);
       if constexpr (kScore) { const float w = g[OFF + j] * d; if (j & 1) q1 = fmaf(w, w, q1); else q0 = fmaf(w, w, q0); }
       else r[OFF + j] = d;
     }
@@ -305,7 +319,7 @@ __device__ __forceinline__ void acc_begin(SmemCtl& S, AccRing& ring, uint32_t tb
 
 // One accumulator = four 16-column quarters, double buffered in a0/a1: the TMEM load of the next quarter is in flight
 // while the CUDA cores work on the current one; the slot returns to the MMA warp once its last quarter is in registers.
-template <bool kInt8, bool kScore, bool kPacked>
+template <int kAcc, bool kScore, bool kPacked>
 __device__ __forceinline__ void acc_step(SmemCtl& S, AccRing& ring, uint32_t tbase, int lane, uint32_t (&a0)[16],
                                          uint32_t (&a1)[16], float (&r)[64], const float (&g)[64], const float4 sc,
                                          float (&p)[4], const bool has_next, const bool skip_math = false) {
@@ -326,13 +340,13 @@ __device__ __forceinline__ void acc_step(SmemCtl& S, AccRing& ring, uint32_t tba
   bool next_ready = true;
   if (has_next) next_ready = mbar_try(next_bar, nphase);
   tmem_ld16(t0 + 16, a1);
-  consume16<kInt8, kScore, kPacked, 0>(a0, r, g, sc.x, p[0]);
+  consume16<kAcc, kScore, kPacked, 0>(a0, r, g, sc.x, p[0]);
   tmem_wait_ld();
   tmem_ld16(t0 + 32, a0);
-  consume16<kInt8, kScore, kPacked, 16>(a1, r, g, sc.y, p[1]);
+  consume16<kAcc, kScore, kPacked, 16>(a1, r, g, sc.y, p[1]);
   tmem_wait_ld();
   tmem_ld16(t0 + 48, a1);
-  consume16<kInt8, kScore, kPacked, 32>(a0, r, g, sc.z, p[2]);
+  consume16<kAcc, kScore, kPacked, 32>(a0, r, g, sc.z, p[2]);
   tmem_wait_ld();
   tc_fence_before();
   __syncwarp();
@@ -343,7 +357,7 @@ __device__ __forceinline__ void acc_step(SmemCtl& S, AccRing& ring, uint32_t tba
     tc_fence_after();
     tmem_ld16(tbase + nslot * kAccCols, a0);
   }
-  consume16<kInt8, kScore, kPacked, 48>(a1, r, g, sc.w, p[3]);
+  consume16<kAcc, kScore, kPacked, 48>(a1, r, g, sc.w, p[3]);
   if (has_next) tmem_wait_ld();
 }
 
@@ -364,7 +378,7 @@ __device__ __forceinline__ void tmem_ld32u(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr));
 }
 // gp: this thread's row of the parked gradient tile, [column quad][128 rows] float4 (quad stride = 128 float4)
-template <bool kInt8, bool kScore, bool kPacked, int OFF>
+template <int kAcc, bool kScore, bool kPacked, int OFF>
 __device__ __forceinline__ void consume32(const uint32_t (&a)[32], float (&r)[64], const float4* gp, const float s0,
                                           const float s1, float& p0, float& p1) {
   if constexpr (!kScore) {
@@ -372,11 +386,11 @@ __device__ __forceinline__ void consume32(const uint32_t (&a)[32], float (&r)[64
     for (int j = 0; j < 32; j += 2) {
       const float s = j < 16 ? s0 : s1;
       if constexpr (kPacked) {
-        const f32x2 d = fma2(pack2(-s, -s), pack2(acc_to_float<kInt8>(a[j]), acc_to_float<kInt8>(a[j + 1])), pack2(r[OFF + j], r[OFF + j + 1]));
+        const f32x2 d = fma2(pack2(-s, -s), acc_pair<kAcc>(a[j], a[j + 1]), pack2(r[OFF + j], r[OFF + j + 1]));
         unpack2(d, r[OFF + j], r[OFF + j + 1]);
       } else {
-        r[OFF + j] = fmaf(-s, acc_to_float<kInt8>(a[j]), r[OFF + j]);
-        r[OFF + j + 1] = fmaf(-s, acc_to_float<kInt8>(a[j + 1]), r[OFF + j + 1]);
+        r[OFF + j] = fmaf(-s, acc_to_float<kAcc>(a[j]), r[OFF + j]);
+        r[OFF + j + 1] = fmaf(-s, acc_to_float<kAcc>(a[j + 1]), r[OFF + j + 1]);
       }
     }
   } else {
@@ -386,8 +400,8 @@ __device__ __forceinline__ void consume32(const uint32_t (&a)[32], float (&r)[64
       const float4 gv = gp[(OFF / 4 + k) * P4V_TILE];
       const float s = k < 4 ? s0 : s1;
       const int j = 4 * k;
-      const float d0 = fmaf(-s, acc_to_float<kInt8>(a[j]), r[OFF + j]), d1 = fmaf(-s, acc_to_float<kInt8>(a[j + 1]), r[OFF + j + 1]);
-      const float d2 = fmaf(-s, acc_to_float<kInt8>(a[j + 2]), r[OFF + j + 2]), d3 = fmaf(-s, acc_to_float<kInt8>(a[j + 3]), r[OFF + j + 3]);
+      const float d0 = fmaf(-s, acc_to_float<kAcc>(a[j]), r[OFF + j]), d1 = fmaf(-s, acc_to_float<kAcc>(a[j + 1]), r[OFF + j + 1]);
+      const float d2 = fmaf(-s, acc_to_float<kAcc>(a[j + 2]), r[OFF + j + 2]), d3 = fmaf(-s, acc_to_float<kAcc>(a[j + 3]), r[OFF + j + 3]);
       const float w0 = gv.x * d0, w1 = gv.y * d1, w2 = gv.z * d2, w3 = gv.w * d3;
       float& qa = q[(k < 4 ? 0 : 2)]; float& qb = q[(k < 4 ? 1 : 3)];
       qa = fmaf(w0, w0, qa); qb = fmaf(w1, w1, qb); qa = fmaf(w2, w2, qa); qb = fmaf(w3, w3, qb);
@@ -401,7 +415,7 @@ __device__ __forceinline__ void accm_begin(SmemCtl& S, AccRing& ring, uint32_t t
   tmem_ld32u(tbase + ring.slot * kAccCols, a0);
   tmem_wait_ld();
 }
-template <bool kInt8, bool kScore, bool kPacked>
+template <int kAcc, bool kScore, bool kPacked>
 __device__ __forceinline__ void accm_step(SmemCtl& S, AccRing& ring, uint32_t tbase, int lane, uint32_t (&a0)[32],
                                           uint32_t (&a1)[32], float (&r)[64], const float4* gp, const float4 sc,
                                           float (&p)[4], const bool has_next, const bool skip_math) {
@@ -420,7 +434,7 @@ __device__ __forceinline__ void accm_step(SmemCtl& S, AccRing& ring, uint32_t tb
   bool next_ready = true;
   if (has_next) next_ready = mbar_try(smem_u32(&S.acc_full[nslot]), nphase);
   tmem_ld32u(t0 + 32, a1);
-  consume32<kInt8, kScore, kPacked, 0>(a0, r, gp, sc.x, sc.y, p[0], p[1]);
+  consume32<kAcc, kScore, kPacked, 0>(a0, r, gp, sc.x, sc.y, p[0], p[1]);
   tmem_wait_ld();
   tc_fence_before();
   __syncwarp();
@@ -431,11 +445,11 @@ __device__ __forceinline__ void accm_step(SmemCtl& S, AccRing& ring, uint32_t tb
     tc_fence_after();
     tmem_ld32u(tbase + nslot * kAccCols, a0);
   }
-  consume32<kInt8, kScore, kPacked, 32>(a1, r, gp, sc.z, sc.w, p[2], p[3]);
+  consume32<kAcc, kScore, kPacked, 32>(a1, r, gp, sc.z, sc.w, p[2], p[3]);
   if (has_next) tmem_wait_ld();
 }
 
-template <bool kInt8, bool kSingle, bool kPacked>
+template <int kAcc, bool kSingle, bool kPacked>
 __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_constant__ SweepParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
@@ -572,10 +586,10 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
           } else if (elect_one()) {
             const uint64_t da = dconst | (uint64_t)a16, db = dconst | (uint64_t)b16;
             const uint32_t d = tmem + kAccBase + slot * kAccCols;
-            umma<kInt8>(d, da, db, (flags & P4V_JOB_FIRST) ? 0u : 1u);
-            if (kb > 32) umma<kInt8>(d, da + 256, db + 256, 1u);
-            if (kb > 64) umma<kInt8>(d, da + 512, db + 512, 1u);
-            if (kb > 96) umma<kInt8>(d, da + 768, db + 768, 1u);
+            umma<(kAcc != kAccF32)>(d, da, db, (flags & P4V_JOB_FIRST) ? 0u : 1u);
+            if (kb > 32) umma<(kAcc != kAccF32)>(d, da + 256, db + 256, 1u);
+            if (kb > 64) umma<(kAcc != kAccF32)>(d, da + 512, db + 512, 1u);
+            if (kb > 96) umma<(kAcc != kAccF32)>(d, da + 768, db + 768, 1u);
             if (sub + 1 == nsub) tc_commit_addr(empty0 + stage * 8);
             if (flags & P4V_JOB_LAST) tc_commit_addr(accf0 + slot * 8);
           }
@@ -684,7 +698,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
         accm_begin(S, ring, tbase, a0);
         for (int gi = 0; gi < P.n_fixed_groups; ++gi) {
           const float4 sc = *reinterpret_cast<const float4*>(&S.fixs[gi][hf * 4]);
-          accm_step<kInt8, false, kPacked>(S, ring, tbase, lane, a0, a1, r, gp, sc, p, gi + 1 < P.n_fixed_groups, dbg2);
+          accm_step<kAcc, false, kPacked>(S, ring, tbase, lane, a0, a1, r, gp, sc, p, gi + 1 < P.n_fixed_groups, dbg2);
         }
       }
       if (P.out != nullptr) {
@@ -713,8 +727,8 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
           const bool noA = (P.cand_noA_mask >> gi) & 1ull;
           const float4 sc = noA ? cb : make_float4(ca.x * cb.x, ca.y * cb.y, ca.z * cb.z, ca.w * cb.w);
           if (ew == 0) TRACE(2, tev, 0);
-          if (gi == P.n_cand_groups - 1) accm_step<kInt8, true, kPacked>(S, ring, tbase, lane, a0, a1, r, gp, sc, p, c + 1 < f.c1, dbg2);
-          else accm_step<kInt8, false, kPacked>(S, ring, tbase, lane, a0, a1, r, gp, sc, p, true, dbg2);
+          if (gi == P.n_cand_groups - 1) accm_step<kAcc, true, kPacked>(S, ring, tbase, lane, a0, a1, r, gp, sc, p, c + 1 < f.c1, dbg2);
+          else accm_step<kAcc, false, kPacked>(S, ring, tbase, lane, a0, a1, r, gp, sc, p, true, dbg2);
           if (ew == 0) { TRACE(2, tev, 1); ++tev; }
         }
         const float tot = reduce4_over_rows(p[0], p[1], p[2], p[3], lane);
@@ -780,7 +794,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
         acc_begin(S, ring, tbase, a0);
         for (int gi = 0; gi < P.n_fixed_groups; ++gi) {
           const float4 sc = *reinterpret_cast<const float4*>(&S.fixs[gi][hf * 4]);
-          acc_step<kInt8, false, kPacked>(S, ring, tbase, lane, a0, a1, r, g, sc, pdummy, gi + 1 < P.n_fixed_groups, dbg2);
+          acc_step<kAcc, false, kPacked>(S, ring, tbase, lane, a0, a1, r, g, sc, pdummy, gi + 1 < P.n_fixed_groups, dbg2);
         }
       }
       if (P.out != nullptr) {
@@ -810,7 +824,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
           if (ew == 0) TRACE(2, tev, 0);
           const float4 ca = *reinterpret_cast<const float4*>(&S.candA[c][hf * 4]);
           const float4 sc = noA ? cb : make_float4(ca.x * cb.x, ca.y * cb.y, ca.z * cb.z, ca.w * cb.w);
-          acc_step<kInt8, true, kPacked>(S, ring, tbase, lane, a0, a1, r, g, sc, p, c + 1 < f.c1, dbg2);
+          acc_step<kAcc, true, kPacked>(S, ring, tbase, lane, a0, a1, r, g, sc, p, c + 1 < f.c1, dbg2);
           if (ew == 0) TRACE(2, tev, 1);
           *reinterpret_cast<float4*>(red_w + (buf * kRedBatch + nb) * kRedCand) = make_float4(p[0], p[1], p[2], p[3]);
           if (ew == 0) TRACE(2, tev, 2);
@@ -888,16 +902,31 @@ int p4v_launch_sweep_tc(const SweepParams& p_in, const P4VJob* host_jobs, int nu
   P4V_REQUIRE(nst >= 2, "sweep: operand tiles do not fit the shared-memory ring");
   p.n_stages = nst;
   const size_t smem = (size_t)nst * per_stage + (size_t)p.resident_bufs * res_bytes + p.cres_bytes + ((sizeof(SmemCtl) + 127) & ~size_t(127)) + (size_t)red_bytes + 256;
-#define P4V_LAUNCH(I8, SG, PK)                                                                         \
+#define P4V_LAUNCH(ACC, SG, PK)                                                                        \
   do {                                                                                                 \
-    P4V_CUDA_OK(cudaFuncSetAttribute(sweep_tc_kernel<I8, SG, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    sweep_tc_kernel<I8, SG, PK><<<grid, kThreads, smem, st>>>(p);                                      \
+    P4V_CUDA_OK(cudaFuncSetAttribute(sweep_tc_kernel<ACC, SG, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    sweep_tc_kernel<ACC, SG, PK><<<grid, kThreads, smem, st>>>(p);                                     \
   } while (0)
-#define P4V_LAUNCH2(I8, SG) do { if (packed) P4V_LAUNCH(I8, SG, true); else P4V_LAUNCH(I8, SG, false); } while (0)
+#define P4V_LAUNCH2(ACC, SG) do { if (packed) P4V_LAUNCH(ACC, SG, true); else P4V_LAUNCH(ACC, SG, false); } while (0)
   p.debug_mode = g_sweep_debug;
   static const bool packed = [] { const char* e = getenv("P4V_PACKED"); return e ? atoi(e) != 0 : true; }();
-  if (p.is_int8) { if (single) P4V_LAUNCH2(true, true); else P4V_LAUNCH2(true, false); }
-  else           { if (single) P4V_LAUNCH2(false, true); else P4V_LAUNCH2(false, false); }
+  static const bool no_magic = getenv("P4V_NO_MAGIC") != nullptr;
+  // s32 accumulators: the add-a-constant convert needs |acc| < 2^22 for every accumulator chain
+  bool magic = p.is_int8 && !no_magic;
+  if (magic) {
+    long long chain = 0, worst = 0;
+    for (int j = 0; j < n_jobs; ++j) {
+      const long long k = host_jobs[j].kb;                       // int8: bytes == elements (per sub-accumulator)
+      if (host_jobs[j].flags & P4V_JOB_FIRST) chain = 0;
+      chain += k;
+      if (chain > worst) worst = chain;
+    }
+    if (worst * (p.acc_elem_bound > 0 ? p.acc_elem_bound : 128 * 128) >= (1ll << 22)) magic = false;
+  }
+  if (p.is_int8) {
+    if (magic) { if (single) P4V_LAUNCH2(kAccMagic, true); else P4V_LAUNCH2(kAccMagic, false); }
+    else       { if (single) P4V_LAUNCH2(kAccI2F, true); else P4V_LAUNCH2(kAccI2F, false); }
+  } else       { if (single) P4V_LAUNCH2(kAccF32, true); else P4V_LAUNCH2(kAccF32, false); }
 #undef P4V_LAUNCH2
 #undef P4V_LAUNCH
   P4V_CUDA_OK(cudaGetLastError());

@@ -29,11 +29,13 @@ class _QuantLinearFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, module, x, weight, bias):
+        ctx.x_meta = (x.shape, x.dtype, x.device) if x.requires_grad else None
         return module._quant_forward_native(x)
 
     @staticmethod
     def backward(ctx, grad_out):
-        return None, None, None, None
+        gx = None if ctx.x_meta is None else torch.zeros(ctx.x_meta[0], dtype=ctx.x_meta[1], device=ctx.x_meta[2])
+        return None, gx, None, None
 
 
 class MinMaxQuantLinear(nn.Linear):

@@ -19,11 +19,13 @@ class _QuantMatMulFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, module, A, B):
+        ctx.meta = [(t.shape, t.dtype, t.device) if t.requires_grad else None for t in (A, B)]
         return module._quant_forward_native(A, B)
 
     @staticmethod
     def backward(ctx, grad_out):
-        return None, None, None
+        g = [None if m is None else torch.zeros(m[0], dtype=m[1], device=m[2]) for m in ctx.meta]
+        return None, g[0], g[1]
 
 
 class MinMaxQuantMatMul(nn.Module):

@@ -76,9 +76,12 @@ class VisionTransformer(nn.Module):
         self.head = nn.Linear(dim, num_classes)
         gen = torch.Generator().manual_seed(seed)
         with torch.no_grad():
-            for p_ in self.parameters():
+            for name_, p_ in self.named_parameters():
                 if p_.dim() > 1:
                     p_.copy_(torch.nn.init.trunc_normal_(torch.empty_like(p_), std=0.02, generator=gen))
+                elif name_.endswith("bias") and "norm" not in name_:
+                    # nn.Linear / nn.Conv2d draw their biases from the global RNG: make the whole net a function of `seed`
+                    p_.copy_(torch.empty_like(p_).uniform_(-0.02, 0.02, generator=gen))
             # synthetic nets have no trained structure: widen activations so that the blocks differ
             for blk in self.blocks:
                 blk.attn.qkv.weight.mul_(4.0)
