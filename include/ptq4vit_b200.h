@@ -116,6 +116,35 @@ P4V_API int p4v_matmul_quant_forward(const p4v_matmul_desc* d, const float* A, c
                              const float* B_interval, const float* split, void* workspace, size_t workspace_bytes,
                              float* out, void* stream);
 
+/* The patch-embedding convolution: ChannelwiseBatchingQuantConv2d with a_bit >= 32 (quant_layers/conv.py:444-614, wired
+ * by configs/PTQ4ViT.py:52-54): one weight step size per output channel, activations left in FP32.  The caller passes
+ * the im2col matrix of the FP32 input (torch.nn.functional.unfold, [images, positions, K], K = in_channels*kh*kw in the
+ * kernel's own order), the kernel as [out_channels, K] and raw_out / raw_grad as [images, out_channels, positions]. */
+typedef struct p4v_conv_desc {
+  int32_t images, out_channels, K, positions;
+  int32_t w_bit;
+  int32_t eq_n;
+  double eq_alpha, eq_beta;
+  int32_t has_bias;
+  int32_t kernel;    /* P4V_KERNEL_TCGEN05 only */
+} p4v_conv_desc;
+P4V_API int p4v_conv_workspace_bytes(const p4v_conv_desc* d, size_t* bytes);
+/* Replaces ChannelwiseBatchingQuantConv2d.calibration_step2() (conv.py:591-603): _initialize_intervals (:482-496) and
+ * _search_best_w_interval (:526-557).  out: w_interval [out_channels] (reference shape oc,1,1,1), score_log NULL or
+ * [eq_n][out_channels].  The search is the same in every round when the activations are not quantised: it runs once. */
+P4V_API int p4v_conv_calibrate(const p4v_conv_desc* d, const float* cols, const float* weight, const float* bias,
+                       const float* raw_out, const float* raw_grad, void* workspace, size_t workspace_bytes,
+                       float* w_interval, float* score_log, void* stream);
+
+/* Integer export of a calibrated module (utils/integer.py:8-129): src [rows, cols] fp32 -> dst one byte per element.
+ * mode 0: int8 = clamp(rne(x / delta), -q, q-1) (quantize_int_weight :8-18, quantize_matmul_input :27-42, plain
+ * activations :64-69); mode 1: the post-GELU twin uint8 layout (:51-62); mode 2: the split-of-softmax twin uint8 layout
+ * (:78-87).  delta[((row / rows_per_block) % n_row_blocks) * n_col_blocks + col / cols_per_block] is the step size of an
+ * element (rows_per_block = 0: one row block). */
+P4V_API int p4v_export_quantized(const float* src, long long rows, long long cols, const float* delta, int rows_per_block,
+                         int n_row_blocks, int cols_per_block, int n_col_blocks, int mode, int bit, float d_neg,
+                         const float* split, void* dst, void* stream);
+
 P4V_API const char* p4v_last_error(void);
 P4V_API int p4v_version(void);
 /* number of kernel launches issued by this library in this process so far (for bench.py's gpu_launches) */

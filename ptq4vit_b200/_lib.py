@@ -27,6 +27,12 @@ class MatMulDesc(C.Structure):
                 ("kernel", C.c_int32)]
 
 
+class ConvDesc(C.Structure):
+    _fields_ = [("images", C.c_int32), ("out_channels", C.c_int32), ("K", C.c_int32), ("positions", C.c_int32),
+                ("w_bit", C.c_int32), ("eq_n", C.c_int32), ("eq_alpha", C.c_double), ("eq_beta", C.c_double),
+                ("has_bias", C.c_int32), ("kernel", C.c_int32)]
+
+
 _P = C.c_void_p
 _SIGNATURES = {
     "p4v_linear_workspace_bytes": [C.POINTER(LinearDesc), C.POINTER(C.c_size_t)],
@@ -43,6 +49,10 @@ _SIGNATURES = {
     "p4v_matmul_calibrate": [C.POINTER(MatMulDesc), _P, _P, _P, _P, _P, C.c_size_t, _P, _P, _P, _P, _P],
     "p4v_matmul_quant_forward_workspace_bytes": [C.POINTER(MatMulDesc), C.POINTER(C.c_size_t)],
     "p4v_matmul_quant_forward": [C.POINTER(MatMulDesc), _P, _P, _P, _P, _P, _P, C.c_size_t, _P, _P],
+    "p4v_conv_workspace_bytes": [C.POINTER(ConvDesc), C.POINTER(C.c_size_t)],
+    "p4v_conv_calibrate": [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, C.c_size_t, _P, _P, _P],
+    "p4v_export_quantized": [_P, C.c_longlong, C.c_longlong, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                             _P, _P, _P],
 }
 EXPORTS = sorted(list(_SIGNATURES) + ["p4v_last_error", "p4v_version", "p4v_launch_count", "p4v_profile_enable", "p4v_profile_collect",
                                      "p4v_profile_collect_kinds",

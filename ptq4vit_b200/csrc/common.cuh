@@ -73,6 +73,9 @@ struct SweepParams {
   int out_residual;         // with out: write y - bias - sum(scale*acc) instead (the current residual e)
   int order;                // 0: tile_m fastest, 1: tile_n fastest
   int is_int8;
+  int R_shared;             // the row operand does not depend on the problem index (conv: kernel planes shared by all images)
+  int row_keys;             // single-segment steps: one score per ROW, partial = [tile][candidate][column half][128 rows]
+  unsigned int red_batch;   // candidates per score-reduction batch of the single-segment steps (filled by the launcher)
   int acc_elem_bound;       // max |row element| * |column element| of the integer operands (0: 128*128); bounds the s32 accumulators
   // shared-memory plan, filled by the launcher
   unsigned int stage_r_bytes, stage_c_bytes, n_stages, resident_bytes, resident_bufs, cres_bytes;
