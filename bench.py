@@ -69,7 +69,10 @@ def is_default_workload(a):
 
 # ------------------------------------------------------------------ unit accounting
 def units_of(module):
+    from ptq4vit_b200.quant_layers.conv import MinMaxQuantConv2d
     from ptq4vit_b200.quant_layers.linear import MinMaxQuantLinear
+    if isinstance(module, MinMaxQuantConv2d):
+        return module.eq_n            # the weight-only search is the same in every round: evaluated (and counted) once
     if isinstance(module, MinMaxQuantLinear):
         return module.search_round * (module.n_H + module.n_a) * module.eq_n
     return module.search_round * ((20 if module.sos else module.eq_n) + module.eq_n)

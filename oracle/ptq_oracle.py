@@ -362,3 +362,60 @@ def make_matmul_fixture(seed, n_img, H, S1, S2, S3, softmax_A=False, grad_scale=
     Y = A @ B
     G = torch.randn(*Y.shape, generator=gen) * grad_scale
     return A, B, Y, G
+
+
+# --------------------------------------------------------------------------
+# Conv2d  (quant_layers/conv.py) -- channel-wise weight search, activations in FP32
+# --------------------------------------------------------------------------
+
+def conv_calibrate(W, bias, x, raw_out, raw_grad, stride, padding=0, dilation=1, w_bit=8, eq_alpha=0.01, eq_beta=1.2, eq_n=100):
+    """ChannelwiseBatchingQuantConv2d.calibration_step2 with a_bit >= 32 (conv.py:591-603): min-max step size per output
+    channel (:487), candidates f_c * delta0 (:593), score = -sum_images mean_positions (g*(y - conv(x, fq(w))))^2 per
+    channel (:545-549), argmax per channel (:554-557).  Returns w_interval [oc,1,1,1] and the score table [eq_n, oc]."""
+    q = 2 ** (w_bit - 1)
+    w_int = W.abs().amax([1, 2, 3], keepdim=True) / (q - 0.5)
+    f = candidate_factors(eq_alpha, eq_beta, eq_n).to(W.device)
+    cands = f.view(-1, 1, 1, 1, 1) * w_int.unsqueeze(0)                  # eq_n+1, oc, 1, 1, 1
+    scores = []
+    for c in range(eq_n):
+        w_sim = (W / cands[c]).round_().clamp_(-q, q - 1).mul_(cands[c])
+        out = F.conv2d(x, w_sim, bias, stride, padding, dilation, 1)
+        s = -(raw_grad * (raw_out - out)) ** 2                            # b, oc, fw, fh
+        scores.append(s.mean(dim=[2, 3]).sum(dim=0))                      # oc
+    scores = torch.stack(scores, 0)
+    best = scores.argmax(dim=0).reshape(1, -1, 1, 1, 1)
+    return torch.gather(cands, 0, best).squeeze(0), scores
+
+
+def make_conv_fixture(seed, n_img, ic, oc, size, k, grad_scale=1e-3, bias=True):
+    gen = torch.Generator().manual_seed(seed)
+    x = torch.randn(n_img, ic, size, size, generator=gen)
+    bound = 1.0 / math.sqrt(ic * k * k)
+    W = (torch.rand(oc, ic, k, k, generator=gen) * 2 - 1) * bound * (1.0 + 2.0 * torch.rand(oc, 1, 1, 1, generator=gen))
+    b = ((torch.rand(oc, generator=gen) * 2 - 1) * bound) if bias else None
+    y = F.conv2d(x, W, b, stride=k)
+    g = torch.randn(*y.shape, generator=gen) * grad_scale
+    return x, W, b, y, g
+
+
+# --------------------------------------------------------------------------
+# Integer export  (utils/integer.py)
+# --------------------------------------------------------------------------
+
+def int_plain(x, interval, qmax):
+    """integer.py:15-17 / :64-67 / :27-42: clamp(rne(x / interval), -qmax, qmax-1) as int8."""
+    return (x / interval).round_().clamp_(-qmax, qmax - 1).to(torch.int8)
+
+
+def int_gelu_twin(x, a_interval, a_neg_interval, qmax):
+    """integer.py:51-62 (uint8 arithmetic, the +128 is added to every element)."""
+    pos = (x / a_interval).round_().clamp_(0, qmax - 1).to(torch.uint8) + 128
+    neg = (x / a_neg_interval).round_().clamp_(-qmax + 1, 0).abs().to(torch.uint8)
+    return pos + neg
+
+
+def int_sos_twin(A, split, A_interval, qmax):
+    """integer.py:78-87"""
+    hi = (A.clamp(split, 1) * (qmax - 1)).round_().clamp_(0, qmax - 1).to(torch.uint8) + 128
+    lo = (A.clamp(0, split) / A_interval).round_().clamp_(0, qmax - 1).to(torch.uint8)
+    return hi + lo

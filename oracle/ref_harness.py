@@ -377,3 +377,23 @@ def time_matmul(A, B, Y, G, sos, eq_n, **mod):
         m.calibration_step2()
     _sync()
     return time.perf_counter() - t0, m.search_round * ((20 if sos else eq_n) + eq_n)
+
+
+def run_conv(x, W, b, y, g, stride, **mod):
+    """ChannelwiseBatchingQuantConv2d(..., a_bit=32).calibration_step2() of the reference (conv.py:444-614)."""
+    import time
+    R = load()
+    kw = dict(COMMON); kw.update(mod)
+    oc, ic, kh, kwid = W.shape
+    m = R.conv.ChannelwiseBatchingQuantConv2d(ic, oc, (kh, kwid), stride=stride, bias=b is not None, a_bit=32, **kw)
+    m.weight.data = W.clone()
+    if b is not None:
+        m.bias.data = b.clone()
+    m.to(_dev())
+    m.raw_input, m.raw_out, m.raw_grad = x.cpu().clone(), y.cpu().clone(), g.cpu().clone()
+    scores = []
+    _sync(); t0 = time.perf_counter()
+    with torch.no_grad(), capture_argmax(scores):
+        m.calibration_step2()
+    _sync()
+    return dict(w_interval=m.w_interval.detach().float().cpu(), scores=scores, seconds=time.perf_counter() - t0, module=m)

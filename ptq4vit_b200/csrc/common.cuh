@@ -75,8 +75,6 @@ struct SweepParams {
   int is_int8;
   int R_shared;             // the row operand does not depend on the problem index (conv: kernel planes shared by all images)
   int row_keys;             // single-segment steps: one score per ROW, partial = [tile][candidate][column half][128 rows]
-  unsigned int red_batch;   // candidates per score-reduction batch of the single-segment steps (filled by the launcher)
-  int acc_elem_bound;       // max |row element| * |column element| of the integer operands (0: 128*128); bounds the s32 accumulators
   // shared-memory plan, filled by the launcher
   unsigned int stage_r_bytes, stage_c_bytes, n_stages, resident_bytes, resident_bufs, cres_bytes;
   long long* trace;         // debug: clock64 timeline of CTA 0 ([3 roles][512 events][4]) or null

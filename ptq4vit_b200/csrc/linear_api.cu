@@ -441,7 +441,6 @@ void fill_sweep(const LinPlan& p, void* ws, const Step& s, SweepParams& sp) {
   sp.n_cand = p.d.eq_n;
   sp.partial = at<float>(ws, p.o_partial);
   sp.is_int8 = p.i8;
-  sp.acc_elem_bound = p.w_qmax * p.a_qmax;
 }
 
 int run_sweep(const LinPlan& p, const Step& s, const SweepParams& sp, cudaStream_t st) {

@@ -211,7 +211,6 @@ void fill_sweep(const MMPlan& p, void* ws, const MStep& s, SweepParams& sp) {
   sp.fix_scale = at<float>(ws, p.o_fix); sp.candA = at<float>(ws, p.o_candA); sp.candB = at<float>(ws, p.o_candB);
   sp.nsg = p.H; sp.sg_mode = P4V_SG_PROBLEM;
   sp.n_cand = p.d.eq_n; sp.partial = at<float>(ws, p.o_partial); sp.is_int8 = p.i8;
-  sp.acc_elem_bound = (p.sos ? p.A_qmax - 1 : p.A_qmax) * p.B_qmax;
 }
 
 int run_sweep(const MMPlan& p, const MStep& s, const SweepParams& sp, cudaStream_t st) {

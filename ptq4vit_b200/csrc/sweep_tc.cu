@@ -45,14 +45,14 @@ constexpr int kTmemCols = 512;
 constexpr int kEpiThreads = 256;
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 128 + kEpiThreads;   // warpgroup 0: producer, MMA, 2 idle warps; warpgroups 1-2: epilogue
-constexpr int kSmemBudget = 208 * 1024;       // ring + resident operands + score reduction buffers + parked gradient tile
+constexpr int kSmemBudget = 200 * 1024;       // ring + resident operand (+ score reduction buffers of the single-segment steps)
 // Score reduction of the single-segment steps: every epilogue thread drops its 4 per-group sums of one candidate into
 // shared memory (one conflict-free 16-byte store, no shuffle chain); every kRedBatch candidates the 256 threads sum
 // the 128 rows of each (candidate, group) in 4 row quarters.  Layout [buffer][candidate][column half][row][4].
 constexpr int kRedBatch = 8;
 constexpr int kRedHalf = P4V_TILE * 4 + 4;    // floats; +4 shifts the second column half by four banks
 constexpr int kRedCand = 2 * kRedHalf;
-constexpr int kGTileBytes = P4V_TILE * P4V_TILE * 4;    // the tile's (scaled) gradient, parked in shared memory
+constexpr int kRedBytes = 2 * kRedBatch * kRedCand * 4;
 
 struct SmemCtl {
   alignas(16) P4VJob jobs[P4V_MAX_JOBS];
@@ -226,15 +226,9 @@ __device__ __forceinline__ bool next_frag(const SweepParams& P, Sched& s, Frag& 
   return true;
 }
 
-// Accumulator element -> float.  kAcc: 0 = fp32 accumulator (integer-valued bf16 operands), 1 = s32 accumulator through
-// the convert unit (I2F: a quarter of the FMA rate, any magnitude), 2 = s32 accumulator with |acc| < 2^22 (the launcher
-// checks the bound of every accumulator chain): 0x4B400000 + acc read as a float is 1.5*2^23 + acc exactly, so the
-// convert is one integer add and one float add, both on full-rate pipes.
-constexpr int kAccF32 = 0, kAccI2F = 1, kAccMagic = 2;
-template <int kAcc>
+template <bool kInt8>
 __device__ __forceinline__ float acc_to_float(uint32_t a) {
-  if constexpr (kAcc == kAccI2F) return __int2float_rn((int)a);
-  else if constexpr (kAcc == kAccMagic) return __uint_as_float(a + 0x4B400000u) - 12582912.f;
+  if constexpr (kInt8) return __int2float_rn((int)a);
   else return __uint_as_float(a);
 }
 
@@ -243,86 +237,38 @@ typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pack2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
 __device__ __forceinline__ void unpack2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
-__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 
-template <int kAcc>
-__device__ __forceinline__ f32x2 acc_pair(uint32_t a0, uint32_t a1) {
-  if constexpr (kAcc == kAccMagic)
-    return add2(pack2(__uint_as_float(a0 + 0x4B400000u), __uint_as_float(a1 + 0x4B400000u)), pack2(-12582912.f, -12582912.f));
-  else return pack2(acc_to_float<kAcc>(a0), acc_to_float<kAcc>(a1));
-}
-
-// ---- epilogue: one accumulator = this thread's row x 64 columns -------------------------------------------------
-// The 64 columns are requested from TMEM with ONE tcgen05.ld.x64 and the request of the NEXT accumulator is in flight
-// while the CUDA cores work on the current one: a TMEM round trip (request -> wait::ld) measured ~350-450 cycles, and the
-// round-1 epilogue paid it two (32-column halves) to four (16-column quarters) times per accumulator with ~100 cycles of
-// math in between -- that, not a pipe, bounded every step (660 / 1800-2600 cycles per accumulator).  Two 64-register
-// buffers alternate; the slot goes back to the MMA warp as soon as its values are in registers, before the math.
-__device__ __forceinline__ void tmem_ld64u(uint32_t taddr, uint32_t (&v)[64]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,"
-      "%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]),
-        "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]),
-        "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]),
-        "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]),
-        "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
-      : "r"(taddr));
-}
-
-// The 64 accumulator columns of one row against the running residual; gp = this thread's row of the gradient tile
-// parked in shared memory, [column quad][128 rows] float4 (needed once per candidate, so it does not live in registers).
+// A quarter of this thread's 64 accumulator columns (16 columns = one scale / score group, already in registers)
+// against the running residual.
 //   kScore == false:  r -= s * acc                        (fixed segments / non-final candidate segments)
-//   kScore == true :  p[q] = sum (g * (r - s*acc))^2 per 16-column scale group q     (final candidate segment; r is kept)
-template <int kAcc, bool kScore, bool kPacked>
-__device__ __forceinline__ void consume64(const uint32_t (&a)[64], float (&r)[64], const float4* gp, const float4 sc, float (&p)[4]) {
+//   kScore == true :  p = sum (g * (r - s*acc))^2          (final candidate segment; r is not modified)
+template <bool kInt8, bool kScore, bool kPacked, int OFF>
+__device__ __forceinline__ void consume16(const uint32_t (&a)[16], float (&r)[64], const float (&g)[64], const float s, float& p) {
+  if constexpr (kPacked) {
+    f32x2 q0 = 0ull, q1 = 0ull;
+    const f32x2 ns = pack2(-s, -s);
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const float s = q == 0 ? sc.x : (q == 1 ? sc.y : (q == 2 ? sc.z : sc.w));
-    if constexpr (kPacked) {
-      const f32x2 ns = pack2(-s, -s);
-      if constexpr (!kScore) {
-#pragma unroll
-        for (int j = 16 * q; j < 16 * q + 16; j += 2) {
-          const f32x2 d = fma2(ns, acc_pair<kAcc>(a[j], a[j + 1]), pack2(r[j], r[j + 1]));
-          unpack2(d, r[j], r[j + 1]);
-        }
+    for (int j = 0; j < 16; j += 2) {
+      const f32x2 f = pack2(acc_to_float<kInt8>(a[j]), acc_to_float<kInt8>(a[j + 1]));
+      const f32x2 d = fma2(ns, f, pack2(r[OFF + j], r[OFF + j + 1]));
+      if constexpr (kScore) {
+        const f32x2 w = mul2(pack2(g[OFF + j], g[OFF + j + 1]), d);
+        if (j & 2) q1 = fma2(w, w, q1); else q0 = fma2(w, w, q0);
       } else {
-        f32x2 q0 = 0ull, q1 = 0ull;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int j = 16 * q + 4 * k;
-          const float4 gv = gp[(4 * q + k) * P4V_TILE];
-          const f32x2 d0 = fma2(ns, acc_pair<kAcc>(a[j], a[j + 1]), pack2(r[j], r[j + 1]));
-          const f32x2 d1 = fma2(ns, acc_pair<kAcc>(a[j + 2], a[j + 3]), pack2(r[j + 2], r[j + 3]));
-          const f32x2 w0 = mul2(pack2(gv.x, gv.y), d0), w1 = mul2(pack2(gv.z, gv.w), d1);
-          q0 = fma2(w0, w0, q0); q1 = fma2(w1, w1, q1);
-        }
-        float x0, y0, x1, y1; unpack2(q0, x0, y0); unpack2(q1, x1, y1);
-        p[q] = (x0 + y0) + (x1 + y1);
-      }
-    } else {
-      if constexpr (!kScore) {
-#pragma unroll
-        for (int j = 16 * q; j < 16 * q + 16; ++j) r[j] = fmaf(-s, acc_to_float<kAcc>(a[j]), r[j]);
-      } else {
-        float q0 = 0.f, q1 = 0.f;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int j = 16 * q + 4 * k;
-          const float4 gv = gp[(4 * q + k) * P4V_TILE];
-          const float w0 = gv.x * fmaf(-s, acc_to_float<kAcc>(a[j]), r[j]), w1 = gv.y * fmaf(-s, acc_to_float<kAcc>(a[j + 1]), r[j + 1]);
-          const float w2 = gv.z * fmaf(-s, acc_to_float<kAcc>(a[j + 2]), r[j + 2]), w3 = gv.w * fmaf(-s, acc_to_float<kAcc>(a[j + 3]), r[j + 3]);
-          q0 = fmaf(w0, w0, q0); q1 = fmaf(w1, w1, q1); q0 = fmaf(w2, w2, q0); q1 = fmaf(w3, w3, q1);
-        }
-        p[q] = q0 + q1;
+        unpack2(d, r[OFF + j], r[OFF + j + 1]);
       }
     }
+    if constexpr (kScore) { float x0, y0, x1, y1; unpack2(q0, x0, y0); unpack2(q1, x1, y1); p = (x0 + y0) + (x1 + y1); }
+  } else {
+    float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float d = fmaf(-s, acc_to_float<kInt8>(a[j]), r[OFF + j]);
+      if constexpr (kScore) { const float w = g[OFF + j] * d; if (j & 1) q1 = fmaf(w, w, q1); else q0 = fmaf(w, w, q0); }
+      else r[OFF + j] = d;
+    }
+    if constexpr (kScore) p = q0 + q1;
   }
 }
 
@@ -343,47 +289,153 @@ __device__ __forceinline__ float reduce4_over_rows(float v0, float v1, float v2,
   return k;
 }
 
-// The epilogue walks the accumulators of the TMEM ring in order.
+// ---- epilogue accumulator pipeline ----------------------------------------------------------------
+// The epilogue walks the accumulators of the TMEM ring in order.  `a0` always holds the first 32 columns
+// of the accumulator about to be consumed (already complete); while the CUDA cores work on one half the
+// TMEM load of the next half is in flight, and the slot goes back to the MMA warp as soon as its second
+// half has landed in registers.
 struct AccRing { uint32_t slot, phase, nslots; };
 
-// wait until the accumulator at the ring head is complete and request this thread's 64 columns of it
-__device__ __forceinline__ void acc_request(SmemCtl& S, const AccRing& ring, uint32_t tbase, uint32_t (&v)[64]) {
+__device__ __forceinline__ void acc_begin(SmemCtl& S, AccRing& ring, uint32_t tbase, uint32_t (&a0)[16]) {
   mbar_wait(&S.acc_full[ring.slot], ring.phase);
   tc_fence_after();
-  tmem_ld64u(tbase + ring.slot * kAccCols, v);
+  tmem_ld16(tbase + ring.slot * kAccCols, a0);
+  tmem_wait_ld();
 }
-// the head's values are in registers: hand the slot back to the MMA warp (one arrival per epilogue warp) and advance
-__device__ __forceinline__ void acc_release(SmemCtl& S, AccRing& ring, int lane) {
+
+// One accumulator = four 16-column quarters, double buffered in a0/a1: the TMEM load of the next quarter is in flight
+// while the CUDA cores work on the current one; the slot returns to the MMA warp once its last quarter is in registers.
+template <bool kInt8, bool kScore, bool kPacked>
+__device__ __forceinline__ void acc_step(SmemCtl& S, AccRing& ring, uint32_t tbase, int lane, uint32_t (&a0)[16],
+                                         uint32_t (&a1)[16], float (&r)[64], const float (&g)[64], const float4 sc,
+                                         float (&p)[4], const bool has_next, const bool skip_math = false) {
+  const uint32_t t0 = tbase + ring.slot * kAccCols;
+  uint32_t nslot = ring.slot + 1, nphase = ring.phase;
+  if (nslot == ring.nslots) { nslot = 0; nphase ^= 1; }
+  if (skip_math) {                 // debug mode 2: handshakes only
+    p[0] = p[1] = p[2] = p[3] = 0.f;
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&S.acc_empty[ring.slot]);
+    ring.slot = nslot; ring.phase = nphase;
+    if (has_next) { mbar_wait(&S.acc_full[ring.slot], ring.phase); tc_fence_after(); }
+    return;
+  }
+  // non-blocking probe of the NEXT accumulator's barrier: its latency hides behind this accumulator's math
+  const uint32_t next_bar = smem_u32(&S.acc_full[nslot]);
+  bool next_ready = true;
+  if (has_next) next_ready = mbar_try(next_bar, nphase);
+  tmem_ld16(t0 + 16, a1);
+  consume16<kInt8, kScore, kPacked, 0>(a0, r, g, sc.x, p[0]);
+  tmem_wait_ld();
+  tmem_ld16(t0 + 32, a0);
+  consume16<kInt8, kScore, kPacked, 16>(a1, r, g, sc.y, p[1]);
+  tmem_wait_ld();
+  tmem_ld16(t0 + 48, a1);
+  consume16<kInt8, kScore, kPacked, 32>(a0, r, g, sc.z, p[2]);
+  tmem_wait_ld();
   tc_fence_before();
   __syncwarp();
-  if (lane == 0) mbar_arrive(&S.acc_empty[ring.slot]);
-  if (++ring.slot == ring.nslots) { ring.slot = 0; ring.phase ^= 1; }
-}
-// One accumulator: `cur` holds its values (requested and waited for); the next one, if any, is requested into `nxt`
-// before the math on `cur` and waited for after it.
-template <int kAcc, bool kScore, bool kPacked>
-__device__ __forceinline__ void acc_step(SmemCtl& S, AccRing& ring, uint32_t tbase, int lane, const uint32_t (&cur)[64],
-                                         uint32_t (&nxt)[64], float (&r)[64], const float4* gp, const float4 sc, float (&p)[4],
-                                         const bool has_next) {
-  acc_release(S, ring, lane);
-  if (has_next) acc_request(S, ring, tbase, nxt);
-  consume64<kAcc, kScore, kPacked>(cur, r, gp, sc, p);
+  if (lane == 0) mbar_arrive(&S.acc_empty[ring.slot]);      // one arrival per epilogue warp
+  ring.slot = nslot; ring.phase = nphase;
+  if (has_next) {
+    if (!next_ready) mbar_wait(&S.acc_full[nslot], nphase);
+    tc_fence_after();
+    tmem_ld16(tbase + nslot * kAccCols, a0);
+  }
+  consume16<kInt8, kScore, kPacked, 48>(a1, r, g, sc.w, p[3]);
   if (has_next) tmem_wait_ld();
 }
-// The two buffers alternate; `flip` says which one holds the current accumulator.
-#define P4V_ACC_STEP(SCORE, SC, PARR, HAS_NEXT)                                                                   \
-  do {                                                                                                             \
-    if (!flip) acc_step<kAcc, SCORE, kPacked>(S, ring, tbase, lane, bufA, bufB, r, gp, SC, PARR, HAS_NEXT);        \
-    else       acc_step<kAcc, SCORE, kPacked>(S, ring, tbase, lane, bufB, bufA, r, gp, SC, PARR, HAS_NEXT);        \
-    flip = !flip;                                                                                                  \
-  } while (0)
-#define P4V_ACC_PRIME()                                                                                            \
-  do {                                                                                                             \
-    if (!flip) acc_request(S, ring, tbase, bufA); else acc_request(S, ring, tbase, bufB);                          \
-    tmem_wait_ld();                                                                                                \
-  } while (0)
 
-template <int kAcc, bool kSingle, bool kPacked>
+
+// ---- multi-segment steps: 32-column halves, gradient tile parked in shared memory ----------------------------
+// Steps with many accumulators per candidate (activation steps) spend one FMA per element on all but the last
+// accumulator, so a 16-column quarter does not cover the latency of the next TMEM load.  Here the gradient tile is
+// NOT kept in registers (it is needed once per candidate); the registers hold two 32-column halves instead.
+__device__ __forceinline__ void tmem_ld32u(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+// gp: this thread's row of the parked gradient tile, [column quad][128 rows] float4 (quad stride = 128 float4)
+template <bool kInt8, bool kScore, bool kPacked, int OFF>
+__device__ __forceinline__ void consume32(const uint32_t (&a)[32], float (&r)[64], const float4* gp, const float s0,
+                                          const float s1, float& p0, float& p1) {
+  if constexpr (!kScore) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      const float s = j < 16 ? s0 : s1;
+      if constexpr (kPacked) {
+        const f32x2 d = fma2(pack2(-s, -s), pack2(acc_to_float<kInt8>(a[j]), acc_to_float<kInt8>(a[j + 1])), pack2(r[OFF + j], r[OFF + j + 1]));
+        unpack2(d, r[OFF + j], r[OFF + j + 1]);
+      } else {
+        r[OFF + j] = fmaf(-s, acc_to_float<kInt8>(a[j]), r[OFF + j]);
+        r[OFF + j + 1] = fmaf(-s, acc_to_float<kInt8>(a[j + 1]), r[OFF + j + 1]);
+      }
+    }
+  } else {
+    float q[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float4 gv = gp[(OFF / 4 + k) * P4V_TILE];
+      const float s = k < 4 ? s0 : s1;
+      const int j = 4 * k;
+      const float d0 = fmaf(-s, acc_to_float<kInt8>(a[j]), r[OFF + j]), d1 = fmaf(-s, acc_to_float<kInt8>(a[j + 1]), r[OFF + j + 1]);
+      const float d2 = fmaf(-s, acc_to_float<kInt8>(a[j + 2]), r[OFF + j + 2]), d3 = fmaf(-s, acc_to_float<kInt8>(a[j + 3]), r[OFF + j + 3]);
+      const float w0 = gv.x * d0, w1 = gv.y * d1, w2 = gv.z * d2, w3 = gv.w * d3;
+      float& qa = q[(k < 4 ? 0 : 2)]; float& qb = q[(k < 4 ? 1 : 3)];
+      qa = fmaf(w0, w0, qa); qb = fmaf(w1, w1, qb); qa = fmaf(w2, w2, qa); qb = fmaf(w3, w3, qb);
+    }
+    p0 = q[0] + q[1]; p1 = q[2] + q[3];
+  }
+}
+__device__ __forceinline__ void accm_begin(SmemCtl& S, AccRing& ring, uint32_t tbase, uint32_t (&a0)[32]) {
+  mbar_wait(&S.acc_full[ring.slot], ring.phase);
+  tc_fence_after();
+  tmem_ld32u(tbase + ring.slot * kAccCols, a0);
+  tmem_wait_ld();
+}
+template <bool kInt8, bool kScore, bool kPacked>
+__device__ __forceinline__ void accm_step(SmemCtl& S, AccRing& ring, uint32_t tbase, int lane, uint32_t (&a0)[32],
+                                          uint32_t (&a1)[32], float (&r)[64], const float4* gp, const float4 sc,
+                                          float (&p)[4], const bool has_next, const bool skip_math) {
+  const uint32_t t0 = tbase + ring.slot * kAccCols;
+  uint32_t nslot = ring.slot + 1, nphase = ring.phase;
+  if (nslot == ring.nslots) { nslot = 0; nphase ^= 1; }
+  if (skip_math) {                 // debug mode 2: handshakes only
+    p[0] = p[1] = p[2] = p[3] = 0.f;
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&S.acc_empty[ring.slot]);
+    ring.slot = nslot; ring.phase = nphase;
+    if (has_next) { mbar_wait(&S.acc_full[ring.slot], ring.phase); tc_fence_after(); }
+    return;
+  }
+  bool next_ready = true;
+  if (has_next) next_ready = mbar_try(smem_u32(&S.acc_full[nslot]), nphase);
+  tmem_ld32u(t0 + 32, a1);
+  consume32<kInt8, kScore, kPacked, 0>(a0, r, gp, sc.x, sc.y, p[0], p[1]);
+  tmem_wait_ld();
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(&S.acc_empty[ring.slot]);      // one arrival per epilogue warp
+  ring.slot = nslot; ring.phase = nphase;
+  if (has_next) {
+    if (!next_ready) mbar_wait(&S.acc_full[nslot], nphase);
+    tc_fence_after();
+    tmem_ld32u(tbase + nslot * kAccCols, a0);
+  }
+  consume32<kInt8, kScore, kPacked, 32>(a1, r, gp, sc.z, sc.w, p[2], p[3]);
+  if (has_next) tmem_wait_ld();
+}
+
+template <bool kInt8, bool kSingle, bool kPacked>
 __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_constant__ SweepParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
@@ -392,9 +444,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
   const uint32_t ringR = smem_u32(smem), ringC = ringR + nst * sR, resR = ringC + nst * sC, resC = resR + P.resident_bufs * resB;
   const size_t ctl_off = (size_t)nst * (sR + sC) + (size_t)P.resident_bufs * resB + cresB;
   SmemCtl& S = *reinterpret_cast<SmemCtl*>(smem + ctl_off);
-  // after the control block: [score reduction buffers (single-segment steps)][gradient tile, 64 KB]
   [[maybe_unused]] float* const red = reinterpret_cast<float*>(smem + ctl_off + ((sizeof(SmemCtl) + 127) & ~size_t(127)));
-  [[maybe_unused]] float* const gtile = red + ((kSingle && !P.row_keys) ? (size_t)2 * P.red_batch * kRedCand : 0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr uint32_t kSlots = kSingle ? 4 : 3;            // single-segment steps do not park the target in TMEM
   constexpr uint32_t kAccBase = kSingle ? 0 : kAccCols;
@@ -522,10 +572,10 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
           } else if (elect_one()) {
             const uint64_t da = dconst | (uint64_t)a16, db = dconst | (uint64_t)b16;
             const uint32_t d = tmem + kAccBase + slot * kAccCols;
-            umma<(kAcc != kAccF32)>(d, da, db, (flags & P4V_JOB_FIRST) ? 0u : 1u);
-            if (kb > 32) umma<(kAcc != kAccF32)>(d, da + 256, db + 256, 1u);
-            if (kb > 64) umma<(kAcc != kAccF32)>(d, da + 512, db + 512, 1u);
-            if (kb > 96) umma<(kAcc != kAccF32)>(d, da + 768, db + 768, 1u);
+            umma<kInt8>(d, da, db, (flags & P4V_JOB_FIRST) ? 0u : 1u);
+            if (kb > 32) umma<kInt8>(d, da + 256, db + 256, 1u);
+            if (kb > 64) umma<kInt8>(d, da + 512, db + 512, 1u);
+            if (kb > 96) umma<kInt8>(d, da + 768, db + 768, 1u);
             if (sub + 1 == nsub) tc_commit_addr(empty0 + stage * 8);
             if (flags & P4V_JOB_LAST) tc_commit_addr(accf0 + slot * 8);
           }
@@ -574,15 +624,16 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
     const uint32_t tstore = tmem + lane_addr + hf * 64;                 // parked residual target (!kSingle)
     const float gs = (P.out && !P.out_residual) ? 1.f : *P.gscale;
     AccRing ring{0u, 0u, kSlots};
+    const bool dbg2 = DBG_MODE(P) & 2;
     [[maybe_unused]] int tev = 0;
+    if constexpr (!kSingle) {
+    // ---------------- several accumulators per candidate (or output mode) ----------------
     float r[64];
-    uint32_t bufA[64], bufB[64];
-    bool flip = false;
-    float4* const gp = reinterpret_cast<float4*>(gtile) + (size_t)(hf * 16) * P4V_TILE + quarter * 32 + lane;
-    const bool want_g = P.out == nullptr;
+    uint32_t a0[32], a1[32];
+    float4* const gp = reinterpret_cast<float4*>(red) + (size_t)(hf * 16) * P4V_TILE + quarter * 32 + lane;
     while (next_frag(P, sched, f)) {
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads));   // previous fragment done with the tables
-      {   // scale tables of this tile's 8 column groups
+      {
         const int sg0 = (P.sg_mode == P4V_SG_COLUMN) ? f.tn * P4V_TILE_CG : (f.p % P.nsg);
         const int sgs = (P.sg_mode == P4V_SG_COLUMN) ? 1 : 0;
         for (int i = et; i < P.n_fixed_groups * P4V_TILE_CG; i += kEpiThreads)
@@ -607,7 +658,7 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
             const float4 yv = *reinterpret_cast<const float4*>(yrow + col0 + j);
             const float4 bv = P.bias ? *reinterpret_cast<const float4*>(P.bias + col0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
             r[j] = yv.x - bv.x; r[j + 1] = yv.y - bv.y; r[j + 2] = yv.z - bv.z; r[j + 3] = yv.w - bv.w;
-            if (want_g) {
+            if (P.out == nullptr) {
               const float4 gv = *reinterpret_cast<const float4*>(grow + col0 + j);
               gp[(j >> 2) * P4V_TILE] = make_float4(gv.x * gs, gv.y * gs, gv.z * gs, gv.w * gs);
             }
@@ -621,20 +672,19 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
               const int col = col0 + j + k;
               const bool ok = row_ok && col < P.N;
               r[j + k] = ok ? (yrow[col] - (P.bias ? P.bias[col] : 0.f)) : 0.f;
-              gq[k] = (ok && want_g) ? grow[col] * gs : 0.f;
+              gq[k] = (ok && P.out == nullptr) ? grow[col] * gs : 0.f;
             }
-            if (want_g) gp[(j >> 2) * P4V_TILE] = make_float4(gq[0], gq[1], gq[2], gq[3]);
+            if (P.out == nullptr) gp[(j >> 2) * P4V_TILE] = make_float4(gq[0], gq[1], gq[2], gq[3]);
           }
         }
       }
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads));   // tables visible
       float p[4] = {0.f, 0.f, 0.f, 0.f};
-      // -- fixed segments: r -= scale * acc --
       if (P.n_fixed_groups > 0) {
-        P4V_ACC_PRIME();
+        accm_begin(S, ring, tbase, a0);
         for (int gi = 0; gi < P.n_fixed_groups; ++gi) {
           const float4 sc = *reinterpret_cast<const float4*>(&S.fixs[gi][hf * 4]);
-          P4V_ACC_STEP(false, sc, p, gi + 1 < P.n_fixed_groups);
+          accm_step<kInt8, false, kPacked>(S, ring, tbase, lane, a0, a1, r, gp, sc, p, gi + 1 < P.n_fixed_groups, dbg2);
         }
       }
       if (P.out != nullptr) {
@@ -647,83 +697,148 @@ __global__ void __launch_bounds__(kThreads, 1) sweep_tc_kernel(const __grid_cons
         }
         continue;
       }
-      if constexpr (!kSingle) {
-        // ---------------- several accumulators per candidate ----------------
-        float* part_base = P.partial + ((size_t)f.tile * P.n_cand) * 32 + quarter * 8 + hf * 4;
-        // park the residual target in TMEM columns [0,128); every candidate starts from it
-        tmem_st32(tstore, r);
-        tmem_st32(tstore + 32, r + 32);
-        tmem_wait_st();
-        if (f.c1 > f.c0) P4V_ACC_PRIME();            // later candidates: requested by the previous candidate's last step
-        for (int c = f.c0; c < f.c1; ++c) {
-          const float4 ca = *reinterpret_cast<const float4*>(&S.candA[c][hf * 4]);
-          if (c > f.c0) {                            // the first candidate starts from the registers
-            tmem_ld32f(tstore, r);
-            tmem_ld32f(tstore + 32, r + 32);
-            tmem_wait_ld();
-          }
-          for (int gi = 0; gi < P.n_cand_groups; ++gi) {
-            const float4 cb = *reinterpret_cast<const float4*>(&S.candB[gi][hf * 4]);
-            const bool noA = (P.cand_noA_mask >> gi) & 1ull;
-            const float4 sc = noA ? cb : make_float4(ca.x * cb.x, ca.y * cb.y, ca.z * cb.z, ca.w * cb.w);
-            if (ew == 0) TRACE(2, tev, 0);
-            if (gi == P.n_cand_groups - 1) P4V_ACC_STEP(true, sc, p, c + 1 < f.c1);
-            else P4V_ACC_STEP(false, sc, p, true);
-            if (ew == 0) { TRACE(2, tev, 1); ++tev; }
-          }
-          const float tot = reduce4_over_rows(p[0], p[1], p[2], p[3], lane);
-          if ((lane & 7) == 0) part_base[(size_t)c * 32 + (lane >> 3)] = tot;
+      float* part_base = P.partial + ((size_t)f.tile * P.n_cand) * 32 + quarter * 8 + hf * 4;
+      // park the residual target in TMEM columns [0,128); every candidate starts from it
+      tmem_st32(tstore, r);
+      tmem_st32(tstore + 32, r + 32);
+      tmem_wait_st();
+      if (f.c1 > f.c0) accm_begin(S, ring, tbase, a0);       // later candidates: prefetched by the previous candidate's last step
+      for (int c = f.c0; c < f.c1; ++c) {
+        const float4 ca = *reinterpret_cast<const float4*>(&S.candA[c][hf * 4]);
+        tmem_ld32f(tstore, r);
+        tmem_ld32f(tstore + 32, r + 32);
+        tmem_wait_ld();
+        for (int gi = 0; gi < P.n_cand_groups; ++gi) {
+          const float4 cb = *reinterpret_cast<const float4*>(&S.candB[gi][hf * 4]);
+          const bool noA = (P.cand_noA_mask >> gi) & 1ull;
+          const float4 sc = noA ? cb : make_float4(ca.x * cb.x, ca.y * cb.y, ca.z * cb.z, ca.w * cb.w);
+          if (ew == 0) TRACE(2, tev, 0);
+          if (gi == P.n_cand_groups - 1) accm_step<kInt8, true, kPacked>(S, ring, tbase, lane, a0, a1, r, gp, sc, p, c + 1 < f.c1, dbg2);
+          else accm_step<kInt8, false, kPacked>(S, ring, tbase, lane, a0, a1, r, gp, sc, p, true, dbg2);
+          if (ew == 0) { TRACE(2, tev, 1); ++tev; }
         }
-      } else {
-        // ---------------- one accumulator per candidate (r stays in registers) ----------------
-        if (f.c1 > f.c0) P4V_ACC_PRIME();
-        const float4 cb = *reinterpret_cast<const float4*>(&S.candB[0][hf * 4]);
-        const bool noA = P.cand_noA_mask & 1ull;
-        if (P.row_keys) {
-          // one score per ROW (channel-wise conv search): this thread's 64 columns, [tile][candidate][column half][128 rows]
-          float* const prow = P.partial + ((size_t)f.tile * P.n_cand) * 256 + hf * P4V_TILE + quarter * 32 + lane;
-          for (int c = f.c0; c < f.c1; ++c) {
-            const float4 ca = *reinterpret_cast<const float4*>(&S.candA[c][hf * 4]);
-            const float4 sc = noA ? cb : make_float4(ca.x * cb.x, ca.y * cb.y, ca.z * cb.z, ca.w * cb.w);
-            P4V_ACC_STEP(true, sc, p, c + 1 < f.c1);
-            prow[(size_t)c * 256] = (p[0] + p[1]) + (p[2] + p[3]);
+        const float tot = reduce4_over_rows(p[0], p[1], p[2], p[3], lane);
+        if ((lane & 7) == 0) part_base[(size_t)c * 32 + (lane >> 3)] = tot;
+      }
+    }
+    } else {
+    // ---------------- one accumulator per candidate ----------------
+    float r[64], g[64];
+    uint32_t a0[16], a1[16];
+
+    while (next_frag(P, sched, f)) {
+      // -- scale tables for this tile's 8 column groups --
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads));   // previous fragment done with the tables
+      {
+        const int sg0 = (P.sg_mode == P4V_SG_COLUMN) ? f.tn * P4V_TILE_CG : (f.p % P.nsg);
+        const int sgs = (P.sg_mode == P4V_SG_COLUMN) ? 1 : 0;
+        for (int i = et; i < P.n_fixed_groups * P4V_TILE_CG; i += kEpiThreads)
+          S.fixs[i >> 3][i & 7] = P.fix_scale[(size_t)(i >> 3) * P.nsg + sg0 + (i & 7) * sgs];
+        for (int i = et; i < P.n_cand_groups * P4V_TILE_CG; i += kEpiThreads)
+          S.candB[i >> 3][i & 7] = P.candB[(size_t)(i >> 3) * P.nsg + sg0 + (i & 7) * sgs];
+        for (int i = et + f.c0 * P4V_TILE_CG; i < f.c1 * P4V_TILE_CG; i += kEpiThreads)
+          S.candA[i >> 3][i & 7] = P.candA[(size_t)(i >> 3) * P.nsg + sg0 + (i & 7) * sgs];
+      }
+      // -- residual target and gradient tile into registers --
+      {
+        const int gm = f.tm * P4V_TILE + quarter * 32 + lane;
+        const int col0 = f.tn * P4V_TILE + hf * 64;
+        const float* yrow = P.Y + (size_t)f.p * P.prob_stride + (size_t)gm * P.ld;
+        const float* grow = P.Gr + (size_t)f.p * P.prob_stride + (size_t)gm * P.ld;
+        const bool row_ok = gm < P.M;
+        if (P.out != nullptr && !P.out_residual) {           // quant_forward: r starts at -bias, output = -r
+#pragma unroll
+          for (int j = 0; j < 64; ++j) {
+            const int col = col0 + j;
+            r[j] = (P.bias && col < P.N) ? -P.bias[col] : 0.f;
+            g[j] = 0.f;
+          }
+        } else if (row_ok && (P.ld & 3) == 0 && (P.prob_stride & 3) == 0 && col0 + 64 <= P.N) {
+#pragma unroll
+          for (int j = 0; j < 64; j += 4) {
+            float4 yv = *reinterpret_cast<const float4*>(yrow + col0 + j);
+            float4 gv = *reinterpret_cast<const float4*>(grow + col0 + j);
+            float4 bv = P.bias ? *reinterpret_cast<const float4*>(P.bias + col0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            r[j] = yv.x - bv.x; r[j + 1] = yv.y - bv.y; r[j + 2] = yv.z - bv.z; r[j + 3] = yv.w - bv.w;
+            g[j] = gv.x * gs; g[j + 1] = gv.y * gs; g[j + 2] = gv.z * gs; g[j + 3] = gv.w * gs;
           }
         } else {
-          float* const part_base_tile = P.partial + ((size_t)f.tile * P.n_cand) * 32;
-          const int rb = P.red_batch;
-          // my slot in the reduction buffers (writer) and my (candidate, row quarter, group) task (reader)
-          float* const red_w = red + hf * kRedHalf + (quarter * 32 + lane) * 4;
-          const int rd_j = et >> 5, rd_q = (et >> 3) & 3, rd_g = et & 7;
-          const float* const red_r = red + rd_j * kRedCand + (rd_g >> 2) * kRedHalf + (rd_q * 32) * 4 + (rd_g & 3);
-          int nb = 0, buf = 0;
-          for (int c = f.c0; c < f.c1; ++c) {
-            if (ew == 0) TRACE(2, tev, 0);
-            const float4 ca = *reinterpret_cast<const float4*>(&S.candA[c][hf * 4]);
-            const float4 sc = noA ? cb : make_float4(ca.x * cb.x, ca.y * cb.y, ca.z * cb.z, ca.w * cb.w);
-            P4V_ACC_STEP(true, sc, p, c + 1 < f.c1);
-            if (ew == 0) TRACE(2, tev, 1);
-            *reinterpret_cast<float4*>(red_w + (buf * rb + nb) * kRedCand) = make_float4(p[0], p[1], p[2], p[3]);
-            if (ew == 0) TRACE(2, tev, 2);
-            if (++nb == rb || c + 1 == f.c1) {
-              asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads));
-              if (rd_j < nb) {                       // sum 32 rows; the start row is rotated per quarter (bank spread)
-                const float* src = red_r + buf * rb * kRedCand;
-                float t0 = 0.f, t1 = 0.f;
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                  t0 += src[((i + 2 * rd_q) & 31) * 4];
-                  t1 += src[((i + 1 + 2 * rd_q) & 31) * 4];
-                }
-                part_base_tile[(size_t)(c + 1 - nb + rd_j) * 32 + (et & 31)] = t0 + t1;
-              }
-              buf ^= 1; nb = 0;
-            }
-            if (ew == 0) { TRACE(2, tev, 3); ++tev; }
+          for (int j = 0; j < 64; ++j) {
+            const int col = col0 + j;
+            const bool ok = row_ok && col < P.N;
+            r[j] = ok ? (yrow[col] - (P.bias ? P.bias[col] : 0.f)) : 0.f;
+            g[j] = ok ? grow[col] * gs : 0.f;
           }
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads));   // tables visible
+
+      // -- fixed segments: r -= scale * acc --
+      float pdummy[4];
+      if (P.n_fixed_groups > 0) {
+        acc_begin(S, ring, tbase, a0);
+        for (int gi = 0; gi < P.n_fixed_groups; ++gi) {
+          const float4 sc = *reinterpret_cast<const float4*>(&S.fixs[gi][hf * 4]);
+          acc_step<kInt8, false, kPacked>(S, ring, tbase, lane, a0, a1, r, g, sc, pdummy, gi + 1 < P.n_fixed_groups, dbg2);
+        }
+      }
+      if (P.out != nullptr) {
+        const int gm = f.tm * P4V_TILE + quarter * 32 + lane;
+        const int col0 = f.tn * P4V_TILE + hf * 64;
+        if (gm < P.M) {
+          float* orow = P.out + (size_t)f.p * P.prob_stride + (size_t)gm * P.ld;
+#pragma unroll
+          for (int j = 0; j < 64; ++j) if (col0 + j < P.N) orow[col0 + j] = P.out_residual ? r[j] : -r[j];
+        }
+        continue;
+      }
+      float* const part_base_tile = P.partial + ((size_t)f.tile * P.n_cand) * 32;
+
+      {
+        // -- one accumulator per candidate --
+        if (f.c1 > f.c0) acc_begin(S, ring, tbase, a0);
+        const float4 cb = *reinterpret_cast<const float4*>(&S.candB[0][hf * 4]);
+        const bool noA = P.cand_noA_mask & 1ull;
+        // my slot in the reduction buffers (writer) and my (candidate, row quarter, group) task (reader)
+        float* const red_w = red + hf * kRedHalf + (quarter * 32 + lane) * 4;
+        const int rd_j = et >> 5, rd_q = (et >> 3) & 3, rd_g = et & 7;
+        const float* const red_r = red + rd_j * kRedCand + (rd_g >> 2) * kRedHalf + (rd_q * 32) * 4 + (rd_g & 3);
+        int nb = 0, buf = 0;
+        for (int c = f.c0; c < f.c1; ++c) {
+          float p[4];
+          if (ew == 0) TRACE(2, tev, 0);
+          const float4 ca = *reinterpret_cast<const float4*>(&S.candA[c][hf * 4]);
+          const float4 sc = noA ? cb : make_float4(ca.x * cb.x, ca.y * cb.y, ca.z * cb.z, ca.w * cb.w);
+          acc_step<kInt8, true, kPacked>(S, ring, tbase, lane, a0, a1, r, g, sc, p, c + 1 < f.c1, dbg2);
+          if (ew == 0) TRACE(2, tev, 1);
+          if (P.row_keys) {        // one score per ROW (channel-wise conv search): [tile][candidate][column half][128 rows]
+            P.partial[((size_t)f.tile * P.n_cand + c) * 256 + hf * P4V_TILE + quarter * 32 + lane] = (p[0] + p[1]) + (p[2] + p[3]);
+            continue;
+          }
+          *reinterpret_cast<float4*>(red_w + (buf * kRedBatch + nb) * kRedCand) = make_float4(p[0], p[1], p[2], p[3]);
+          if (ew == 0) TRACE(2, tev, 2);
+          if (++nb == kRedBatch || c + 1 == f.c1) {
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads));
+            if (rd_j < nb) {                       // sum 32 rows; the start row is rotated per quarter (bank spread)
+              const float* src = red_r + buf * kRedBatch * kRedCand;
+              float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                t0 += src[((i + 2 * rd_q) & 31) * 4];
+                t1 += src[((i + 1 + 2 * rd_q) & 31) * 4];
+              }
+              part_base_tile[(size_t)(c + 1 - nb + rd_j) * 32 + (et & 31)] = t0 + t1;
+            }
+            buf ^= 1; nb = 0;
+          }
+          if (ew == 0) { TRACE(2, tev, 3); ++tev; }
         }
       }
     }
   }
+
+    }
   // ---- teardown ----
   tc_fence_before();
   __syncthreads();
@@ -746,6 +861,7 @@ int p4v_launch_sweep_tc(const SweepParams& p_in, const P4VJob* host_jobs, int nu
   P4V_REQUIRE(p.n_fixed_groups <= P4V_MAX_GROUPS && p.n_cand_groups <= P4V_MAX_GROUPS, "sweep: too many segment groups");
   P4V_REQUIRE(p.n_cand <= P4V_MAX_CAND && p.n_cand >= 1, "sweep: bad candidate count");
   P4V_REQUIRE(p.out != nullptr ? (p.n_cand == 1 && p.n_cand_jobs == 0) : p.n_cand_groups >= 1, "sweep: bad mode");
+  P4V_REQUIRE(!p.row_keys || (p.n_cand_groups == 1 && p.out == nullptr), "sweep: per-row scores need a single-segment step");
   const long long tiles = (long long)p.P * p.tiles_m * p.tiles_n;
   const long long units = tiles * p.n_cand;
   int grid = (int)(units < num_sms ? units : num_sms);
@@ -769,49 +885,24 @@ int p4v_launch_sweep_tc(const SweepParams& p_in, const P4VJob* host_jobs, int nu
   const uint32_t per_stage = p.stage_r_bytes + p.stage_c_bytes;
   P4V_REQUIRE(per_stage > 0, "sweep: no streamed operand");
   const bool single = p.n_cand_groups == 1 && p.out == nullptr;
-  P4V_REQUIRE(!p.row_keys || single, "sweep: per-row scores need a single-segment step");
-  // after the ring: score reduction buffers (single-segment steps, batches of 8 or 4 candidates) + the parked gradient tile
-  auto plan = [&](unsigned batch, int& nst_out, unsigned& rbufs) {
-    const long long red_bytes = (single && !p.row_keys ? 2ll * batch * kRedCand * 4 : 0) + (p.out == nullptr ? kGTileBytes : 0);
-    rbufs = 2;                              // double buffered when that leaves a useful ring, else one buffer (a bubble per tile)
-    if ((kSmemBudget - 2 * (long long)res_bytes - red_bytes - (long long)p.cres_bytes) / per_stage < 3) rbufs = 1;
-    nst_out = (int)((kSmemBudget - (long long)rbufs * res_bytes - red_bytes - (long long)p.cres_bytes) / per_stage);
-    return red_bytes;
-  };
-  int nst = 0; unsigned rbufs = 2;
-  p.red_batch = kRedBatch;
-  long long red_bytes = plan(p.red_batch, nst, rbufs);
-  if (single && !p.row_keys && nst < 4) { p.red_batch = kRedBatch / 2; red_bytes = plan(p.red_batch, nst, rbufs); }
-  p.resident_bufs = rbufs;
+  const long long red_bytes = single ? kRedBytes : (p.out == nullptr ? (long long)P4V_TILE * P4V_TILE * 4 : 0);   // score reduction buffers / parked gradient tile
+  p.resident_bufs = 2;                      // double buffered when that leaves a useful ring, else one buffer (a bubble per tile)
+  if ((kSmemBudget - 2 * (long long)res_bytes - red_bytes - (long long)p.cres_bytes) / per_stage < 3) p.resident_bufs = 1;
+  int nst = (int)((kSmemBudget - (long long)p.resident_bufs * res_bytes - red_bytes - (long long)p.cres_bytes) / per_stage);
   if (nst > kMaxStages) nst = kMaxStages;
   P4V_REQUIRE(nst >= 2, "sweep: operand tiles do not fit the shared-memory ring");
   p.n_stages = nst;
   const size_t smem = (size_t)nst * per_stage + (size_t)p.resident_bufs * res_bytes + p.cres_bytes + ((sizeof(SmemCtl) + 127) & ~size_t(127)) + (size_t)red_bytes + 256;
-#define P4V_LAUNCH(ACC, SG, PK)                                                                        \
+#define P4V_LAUNCH(I8, SG, PK)                                                                         \
   do {                                                                                                 \
-    P4V_CUDA_OK(cudaFuncSetAttribute(sweep_tc_kernel<ACC, SG, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    sweep_tc_kernel<ACC, SG, PK><<<grid, kThreads, smem, st>>>(p);                                     \
+    P4V_CUDA_OK(cudaFuncSetAttribute(sweep_tc_kernel<I8, SG, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    sweep_tc_kernel<I8, SG, PK><<<grid, kThreads, smem, st>>>(p);                                      \
   } while (0)
-#define P4V_LAUNCH2(ACC, SG) do { if (packed) P4V_LAUNCH(ACC, SG, true); else P4V_LAUNCH(ACC, SG, false); } while (0)
+#define P4V_LAUNCH2(I8, SG) do { if (packed) P4V_LAUNCH(I8, SG, true); else P4V_LAUNCH(I8, SG, false); } while (0)
   p.debug_mode = g_sweep_debug;
   static const bool packed = [] { const char* e = getenv("P4V_PACKED"); return e ? atoi(e) != 0 : true; }();
-  static const bool no_magic = getenv("P4V_NO_MAGIC") != nullptr;
-  // s32 accumulators: the add-a-constant convert needs |acc| < 2^22 for every accumulator chain
-  bool magic = p.is_int8 && !no_magic;
-  if (magic) {
-    long long chain = 0, worst = 0;
-    for (int j = 0; j < n_jobs; ++j) {
-      const long long k = host_jobs[j].kb;                       // int8: bytes == elements (per sub-accumulator)
-      if (host_jobs[j].flags & P4V_JOB_FIRST) chain = 0;
-      chain += k;
-      if (chain > worst) worst = chain;
-    }
-    if (worst * (p.acc_elem_bound > 0 ? p.acc_elem_bound : 128 * 128) >= (1ll << 22)) magic = false;
-  }
-  if (p.is_int8) {
-    if (magic) { if (single) P4V_LAUNCH2(kAccMagic, true); else P4V_LAUNCH2(kAccMagic, false); }
-    else       { if (single) P4V_LAUNCH2(kAccI2F, true); else P4V_LAUNCH2(kAccI2F, false); }
-  } else       { if (single) P4V_LAUNCH2(kAccF32, true); else P4V_LAUNCH2(kAccF32, false); }
+  if (p.is_int8) { if (single) P4V_LAUNCH2(true, true); else P4V_LAUNCH2(true, false); }
+  else           { if (single) P4V_LAUNCH2(false, true); else P4V_LAUNCH2(false, false); }
 #undef P4V_LAUNCH2
 #undef P4V_LAUNCH
   P4V_CUDA_OK(cudaGetLastError());

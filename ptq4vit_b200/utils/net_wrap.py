@@ -9,7 +9,7 @@ MODULE_TYPES = {"qkv": "qlinear_qkv", "proj": "qlinear_proj", "fc1": "qlinear_ML
                 "reduction": "qlinear_reduction"}
 
 
-def wrap_modules_in_net(net, cfg, wrap_conv=False):
+def wrap_modules_in_net(net, cfg, wrap_conv=True):
     wrapped_modules = {}
     module_dict = {}
     for name, m in list(net.named_modules()):
@@ -27,7 +27,7 @@ def wrap_modules_in_net(net, cfg, wrap_conv=False):
             new_m.weight.data = m.weight.data
             new_m.bias = m.bias
             new_m.to(m.weight.device)
-        if isinstance(m, nn.Linear):
+        elif isinstance(m, nn.Linear):
             new_m = cfg.get_module(MODULE_TYPES[leaf], m.in_features, m.out_features)
             new_m.weight.data = m.weight.data
             new_m.bias = m.bias

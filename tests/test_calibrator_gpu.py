@@ -34,7 +34,7 @@ def _net():
     return net
 
 
-def _ours(sequential=False, capture="auto", keep=None, wrap_conv=False):
+def _ours(sequential=False, capture="auto", keep=None, wrap_conv=True):
     from ptq4vit_b200.configs import PTQ4ViT as cfg
     from ptq4vit_b200.utils import quant_calib as Q
     from ptq4vit_b200.utils.net_wrap import wrap_modules_in_net
@@ -177,7 +177,7 @@ def test_base_batching_quant_calib_l2():
     for d in (cfg.ptqsl_linear_kwargs, cfg.ptqsl_matmul_kwargs, cfg.ptqsl_conv2d_kwargs):
         d["metric"] = "L2_norm"; d["search_round"] = 1
     net = _net()
-    wrapped = wrap_modules_in_net(net, cfg)
+    wrapped = wrap_modules_in_net(net, cfg, wrap_conv=True)
     cal = Q.QuantCalibrator(net, wrapped, RH.ListLoader(RH.tiny_images()), sequential=False)
     cal.batch_size = 4
     cal.batching_quant_calib()

@@ -52,7 +52,9 @@ def test_wrap_counts_match_reference_module_inventory():
     importlib.reload(cfg)
     net = VisionTransformer(img_size=32, patch=16, dim=64, depth=2, num_heads=2, num_classes=10)
     wrapped = wrap_modules_in_net(net, cfg)
-    assert len(wrapped) == 2 * 6 + 1                          # per block qkv, proj, fc1, fc2, matmul1, matmul2 + head
+    assert len(wrapped) == 1 + 2 * 6 + 1                      # patch-embedding conv + per block qkv, proj, fc1, fc2, matmul1, matmul2 + head
+    from ptq4vit_b200.quant_layers.conv import ChannelwiseBatchingQuantConv2d
+    assert isinstance(net.patch_embed.proj, ChannelwiseBatchingQuantConv2d) and net.patch_embed.proj.n_V == 64 and net.patch_embed.proj.a_bit == 32
     assert isinstance(net.blocks[0].attn.matmul2, M.SoSPTQSLBatchingQuantMatMul)
     out = net(torch.randn(2, 3, 32, 32))
     assert out.shape == (2, 10)
