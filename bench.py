@@ -396,6 +396,7 @@ def main():
                 if hasattr(m, "calibrated"):
                     del m.calibrated
                 m.mode = "raw"
+                m.raw_input = m.raw_out = m.raw_grad = None      # calibration_step2 deletes them (linear.py:554)
             sync_all()
             cal.batching_quant_calib()
             t = cal.timings

@@ -175,7 +175,7 @@ class ChannelwiseBatchingQuantConv2d(PTQSLQuantConv2d):
                                           ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)),
                    "p4v_conv_calibrate")
         self.w_interval = w_int.view(oc, 1, 1, 1)
-        self.a_interval = None
+        self.a_interval = (x.abs().max() / (self.a_qmax - 0.5)).detach().view(1)   # conv.py:490-496 (unused when a_bit >= 32)
         self.last_scores = [log.view(self.eq_n, oc)] * int(self.search_round) if log is not None else None
         self.calibrated = True
         del self.raw_input, self.raw_out, self.raw_grad

@@ -27,19 +27,22 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "calib
 GRID = (1.2 - 0.01) / 100
 
 
-def _net():
-    from ptq4vit_b200.utils.models import VisionTransformer
-    net = VisionTransformer(**RH.TINY_VIT).cuda().eval()
-    RH.add_target_noise(net, 8, RH.TINY_VIT["num_classes"])
+TINY_SWIN = dict(img_size=32, patch=4, dim=32, depths=(2, 2), num_heads=(2, 4), window_size=4, num_classes=10)
+
+
+def _net(kind="vit"):
+    from ptq4vit_b200.utils.models import SwinTransformer, VisionTransformer
+    net = (SwinTransformer(**TINY_SWIN) if kind == "swin" else VisionTransformer(**RH.TINY_VIT)).cuda().eval()
+    RH.add_target_noise(net, 8, 10)
     return net
 
 
-def _ours(sequential=False, capture="auto", keep=None, wrap_conv=True):
+def _ours(sequential=False, capture="auto", keep=None, wrap_conv=True, kind="vit"):
     from ptq4vit_b200.configs import PTQ4ViT as cfg
     from ptq4vit_b200.utils import quant_calib as Q
     from ptq4vit_b200.utils.net_wrap import wrap_modules_in_net
     importlib.reload(cfg)
-    net = _net()
+    net = _net(kind)
     wrapped = wrap_modules_in_net(net, cfg, wrap_conv=wrap_conv)
     cal = Q.HessianQuantCalibrator(net, wrapped, RH.ListLoader(RH.tiny_images()), sequential=sequential, batch_size=4, capture=capture)
     cal.keep_captured = keep
@@ -56,6 +59,8 @@ def _count_diff(got, ref, what, max_frac, max_steps=3):
         if name not in got:
             continue
         for key, rv in d.items():
+            if key not in got[name]:
+                continue
             gv = got[name][key].reshape(-1).numpy().astype(np.float64); rv = rv.reshape(-1).numpy().astype(np.float64)
             assert gv.shape == rv.shape, f"{what}: {name}.{key} shape {gv.shape} vs {rv.shape}"
             rel = np.abs(gv - rv) / np.abs(rv)
@@ -98,6 +103,24 @@ def test_batching_quant_calib_matches_reference_calibrator_on_gpu():
     with torch.no_grad():
         ours_out = net(RH.tiny_images().cuda()[:4])
     assert torch.isfinite(ours_out).all()
+
+
+def test_swin_windowed_attention_and_reduction_match_reference_calibrator():
+    """BASELINE.json configs[4] geometry in small: shifted windows, window attention MatMuls with the batch dimension
+    images x windows (reference utils/models.py:28-56) and the `reduction` Linear of patch merging (utils/net_wrap.py:42)."""
+    if not RH.available():
+        pytest.skip("needs the staged reference (baseline/_ref)")
+    snap_ours, snap_ref = {}, {}
+    got, net, wrapped, cal = _ours(keep=snap_ours, kind="swin")
+    assert any(n.endswith("downsample.reduction") for n in wrapped) and any("layers.0.blocks.1.attn.matmul1" == n for n in wrapped)
+    ref, _, _ = RH.run_reference_calibrator(_net("swin"), RH.tiny_images(), batch_size=4, sequential=False, snapshot=snap_ref)
+    assert set(ref) == set(got)
+    for name, d in snap_ours.items():
+        for key, t in d.items():
+            r = snap_ref[name][key].to(t.device)
+            assert float((t - r).abs().max()) <= 1e-5 * float(r.abs().max()) + 1e-30, f"captured {name}.{key}"
+    bad, n = _count_diff(got, ref, "swin vs reference on GPU", max_frac=0.05)
+    print(f"[calibrator swin] {len(got)} modules (window attention + patch merging), {bad}/{n} step sizes differ")
 
 
 def test_batching_quant_calib_matches_cpu_golden():
