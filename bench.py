@@ -521,6 +521,9 @@ def main():
         dist.destroy_process_group()
     del work
     torch.cuda.empty_cache()
+    from ptq4vit_b200.utils.models import _ZOO
+    if a.model not in _ZOO:          # the reference legs below are laid out for the ViT / DeiT layer types
+        a.no_ref_gpu = a.no_cpu = True
     if world == 1 and not a.no_ref_gpu:
         try:
             samples, kind = reference_rates(a, on_gpu=True, eq_n=100)

@@ -97,7 +97,7 @@ __global__ void conv_reduce_kernel(const float* __restrict__ partial, int P, int
     for (int tl = 0; tl < tiles_l; ++tl) {
       // tile index of the sweep: order 0 -> t = tn * tiles_m + tm inside a problem
       const size_t tile = (size_t)p * tiles_o * tiles_l + (size_t)tl * tiles_o + to;
-      const float* base = partial + (tile * n_cand + c) * 256;
+      const float* base = partial + (tile * n_cand + c) * 256;          // [column half][128 rows]
       acc += (double)base[r] + (double)base[128 + r];
     }
   sums[(size_t)c * O + o] = acc;

@@ -100,12 +100,13 @@ __global__ void make_gscale_kernel(const int* key, float* gscale) {
 // P * chunks, plane groups): rows are the fastest index so that the 16-byte stores of a warp are contiguous in the
 // image; the source values are loaded once and quantised for every plane (candidate step size) of the subset.
 template <bool kInt8>
-__global__ void quant_image_kernel(const QuantImageArgs a, int chunks_total) {
+__global__ void quant_image_kernel(const QuantImageArgs a, int chunks_total, int row_blocks) {
   const int rows_pad = a.tiles * P4V_TILE;
-  const int row_p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row_p = (int)(blockIdx.x % row_blocks) * blockDim.x + threadIdx.x;      // rows fastest, then (problem, chunk)
   if (row_p >= rows_pad) return;
-  const int p = blockIdx.y / chunks_total;
-  int chunk = blockIdx.y % chunks_total;
+  const unsigned pc = blockIdx.x / row_blocks;
+  const int p = (int)(pc / chunks_total);
+  int chunk = (int)(pc % chunks_total);
   constexpr int epc = kInt8 ? 16 : 8;          // elements per 16-byte chunk
   int s = 0;
   while (true) {
@@ -426,14 +427,15 @@ int p4v_quant_image(const QuantImageArgs& a_in, cudaStream_t st) {
   const int chunks_total = (int)(a.tile_bytes / P4V_TILE / 16);     // every segment is padded to 32 B
   const int rows_pad = a.tiles * P4V_TILE;
   if (rows_pad == 0 || chunks_total == 0 || a.n_planes == 0 || a.P == 0) return 0;
-  P4V_REQUIRE((long long)a.P * chunks_total <= 65535 && a.n_planes <= 65535, "quant_image: grid too large");
-  const long long blocks_xy = (long long)p4v_cdiv(rows_pad, 128) * a.P * chunks_total;
+  const int row_blocks = p4v_cdiv(rows_pad, 128);
+  const long long blocks_xy = (long long)row_blocks * a.P * chunks_total;
+  P4V_REQUIRE(blocks_xy <= 0x7fffffffll && a.n_planes <= 65535, "quant_image: grid too large");
   long long zg = (4096 + blocks_xy - 1) / blocks_xy;        // enough blocks to fill the GPU, otherwise all planes per thread
   if (zg > a.n_planes) zg = a.n_planes;
   if (zg < 1) zg = 1;
-  dim3 grid(p4v_cdiv(rows_pad, 128), a.P * chunks_total, (unsigned)zg);
-  if (a.is_int8) quant_image_kernel<true><<<grid, 128, 0, st>>>(a, chunks_total);
-  else quant_image_kernel<false><<<grid, 128, 0, st>>>(a, chunks_total);
+  dim3 grid((unsigned)blocks_xy, 1, (unsigned)zg);
+  if (a.is_int8) quant_image_kernel<true><<<grid, 128, 0, st>>>(a, chunks_total, row_blocks);
+  else quant_image_kernel<false><<<grid, 128, 0, st>>>(a, chunks_total, row_blocks);
   p4v_count_launch();
   P4V_CUDA_OK(cudaGetLastError());
   return 0;
