@@ -29,6 +29,8 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 os.environ.setdefault("TQDM_DISABLE", "1")
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "NONE"          # keep stdout to the one JSON line (NCCL prints its version banner there)
 
 import torch  # noqa: E402
 

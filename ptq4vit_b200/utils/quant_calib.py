@@ -154,6 +154,7 @@ def unpack_result(module, row, heads=None):
     if isinstance(module, MinMaxQuantConv2d):
         nw = module.out_channels
         module.w_interval = row[:nw].clone().view(nw, 1, 1, 1)
+        module.a_interval = row[nw:nw + 1].clone()
     elif isinstance(module, MinMaxQuantLinear):
         nw = module.n_V * module.n_H
         module.w_interval = row[:nw].clone().view(module.n_V, 1, module.n_H, 1)
@@ -175,7 +176,7 @@ def result_width(modules):
     w = 1
     for m in modules:
         if isinstance(m, MinMaxQuantConv2d):
-            w = max(w, m.out_channels)
+            w = max(w, m.out_channels + 1)      # per-channel weight step sizes + the (unused) activation step size
         elif isinstance(m, MinMaxQuantLinear):
             w = max(w, m.n_V * m.n_H + m.n_a)
         else:

@@ -95,11 +95,16 @@ def _gather_worker(rank, world, port, ret):
     for i in range(5):
         mods[f"lin{i}"] = L.PTQSLBatchingQuantLinear(32, 32, n_V=2, n_H=2, n_a=1)
     mods["mm"] = M.PTQSLBatchingQuantMatMul()
+    from ptq4vit_b200.quant_layers.conv import ChannelwiseBatchingQuantConv2d
+    mods["conv"] = ChannelwiseBatchingQuantConv2d(3, 40, 4, stride=4, a_bit=32)    # widest row of this set: 40 + 1
     names = list(mods)
     owner = Q.shard_modules(names, [1.0 + i for i in range(len(names))], world)
     for i, n in enumerate(names):
         if owner[n] == rank:
-            if n == "mm":
+            if n == "conv":
+                mods[n].w_interval = torch.arange(40, dtype=torch.float32).view(40, 1, 1, 1) + 0.5
+                mods[n].a_interval = torch.tensor([7.0])
+            elif n == "mm":
                 mods[n].n_G_B = 4
                 mods[n].A_interval = torch.full((1, 4, 1, 1, 1, 1, 1), 10.0 + i)
                 mods[n].B_interval = torch.full((1, 4, 1, 1, 1, 1, 1), 20.0 + i)
@@ -109,6 +114,7 @@ def _gather_worker(rank, world, port, ret):
     cal._gather(owner)
     ok = all(float(mods[f"lin{i}"].w_interval.mean()) == float(i) and float(mods[f"lin{i}"].a_interval) == 100.0 + i for i in range(5))
     ok = ok and float(mods["mm"].B_interval.mean()) == 25.0 and mods["mm"].A_interval.shape == (1, 4, 1, 1, 1, 1, 1)
+    ok = ok and mods["conv"].w_interval.shape == (40, 1, 1, 1) and float(mods["conv"].w_interval[39]) == 39.5 and float(mods["conv"].a_interval) == 7.0
     ret[rank] = ok
     dist.destroy_process_group()
 
