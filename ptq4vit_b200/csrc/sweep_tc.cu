@@ -897,6 +897,8 @@ int p4v_launch_sweep_tc(const SweepParams& p_in, const P4VJob* host_jobs, int nu
   if ((kSmemBudget - 2 * (long long)res_bytes - red_bytes - (long long)p.cres_bytes) / per_stage < 3) p.resident_bufs = 1;
   int nst = (int)((kSmemBudget - (long long)p.resident_bufs * res_bytes - red_bytes - (long long)p.cres_bytes) / per_stage);
   if (nst > kMaxStages) nst = kMaxStages;
+  { static const int cap = [] { const char* e = getenv("P4V_MAX_STAGES"); return e ? atoi(e) : 0; }();   // experiment knob
+    if (cap >= 2 && nst > cap) nst = cap; }
   P4V_REQUIRE(nst >= 2, "sweep: operand tiles do not fit the shared-memory ring");
   p.n_stages = nst;
   const size_t smem = (size_t)nst * per_stage + (size_t)p.resident_bufs * res_bytes + p.cres_bytes + ((sizeof(SmemCtl) + 127) & ~size_t(127)) + (size_t)red_bytes + 256;
