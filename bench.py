@@ -502,7 +502,8 @@ def main():
                 "traffic_note": tr.get("note") if traffic is not None else "ncu DRAM bytes are recorded for the default workload only",
                 "by_kind": by_kind,
                 "longest_launch": {"kind": top_kind, "ms": prof[9], "achieved": top_ach, "peak": top_peak, "frac": top_ach / top_peak,
-                                   "peak_is": "burst (a launch timed alone)"},
+                                   "peak_is": "burst (a launch timed alone)",
+                                   "traffic": tr.get("longest_launch_dram_bytes") if traffic is not None else None},
                 "note": "achieved = EXECUTED tensor-core operations (slab-incremental search: only the K segment a candidate changes is "
                         "multiplied; Gram GEMM: three bf16 term products) / CUDA-event time of the launches of that kind on this rank; "
                         "peak = " + peak_src + "; int8 launches are held against 2x the measured bf16 rate (stated, not measured: "
