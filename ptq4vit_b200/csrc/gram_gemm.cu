@@ -51,7 +51,7 @@ __device__ __forceinline__ bool mbar_try(uint32_t addr, uint32_t parity) {
 __device__ __noinline__ void mbar_wait_slow(uint32_t addr, uint32_t parity) {     // bounded: a protocol bug traps, never hangs
   const long long t0 = clock64();
   while (!mbar_try(addr, parity))
-    if (clock64() - t0 > 4000000000ll) {
+    if (clock64() - t0 > 20000000000ll) {
       printf("ptq4vit_b200 gram gemm: mbarrier wait timed out (block %d thread %d smem 0x%x parity %u)\n", (int)blockIdx.x,
              (int)threadIdx.x, addr, parity);
       __trap();

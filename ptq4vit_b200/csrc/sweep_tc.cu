@@ -95,7 +95,9 @@ __device__ __forceinline__ bool mbar_try(uint32_t addr, uint32_t parity) {
                "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must surface as a trapped launch (cudaErrorLaunchFailure), never as a hung GPU.
+// Bounded wait: a protocol bug must surface as a trapped launch (cudaErrorLaunchFailure), never as a hung GPU.  The bound
+// is ~10 s of SM clocks: clock64 keeps counting while a context is time-sliced (MPS, profilers), a legitimate wait of a
+// sub-millisecond kernel must never reach it.
 [[noreturn]] __device__ __noinline__ void mbar_timeout(uint32_t addr, uint32_t parity) {
   printf("ptq4vit_b200 sweep: mbarrier wait timed out (block %d thread %d smem 0x%x parity %u)\n",
          (int)blockIdx.x, (int)threadIdx.x, addr, parity);
@@ -105,14 +107,14 @@ __device__ __forceinline__ bool mbar_try(uint32_t addr, uint32_t parity) {
 __device__ __noinline__ void mbar_wait_slow(uint32_t addr, uint32_t parity) {
   const long long t0 = clock64();
   while (!mbar_try(addr, parity))
-    if (clock64() - t0 > 4000000000ll) mbar_timeout(addr, parity);
+    if (clock64() - t0 > 20000000000ll) mbar_timeout(addr, parity);
 }
 __device__ __forceinline__ void mbar_wait(void* bar, uint32_t parity) {     // fully inline: safe with many live registers
   const uint32_t addr = smem_u32(bar);
   if (mbar_try(addr, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try(addr, parity))
-    if (clock64() - t0 > 4000000000ll) mbar_timeout(addr, parity);
+    if (clock64() - t0 > 20000000000ll) mbar_timeout(addr, parity);
 }
 __device__ __forceinline__ void mbar_wait_addr(uint32_t addr, uint32_t parity) {
   if (!mbar_try(addr, parity)) mbar_wait_slow(addr, parity);

@@ -1,7 +1,7 @@
 """Full-size (BASELINE.json configs[1]: ViT-B/224, 32 images) checks through size-independent properties.
 
-The CPU oracle needs minutes per candidate at these sizes, so the full-size layers are checked through
-properties of the search itself (reference: quant_layers/linear.py:455-533, matmul.py:483-563):
+The comparison with the reference itself at these sizes lives in tests/test_reference_gpu.py (the unmodified classes
+on the same GPU); here the full-size layers are additionally checked through properties of the search itself (reference: quant_layers/linear.py:455-533, matmul.py:483-563):
   * two independent formulations of the weight steps (slab sweep on the tensor cores vs. the normal-equation
     form) must choose the same step sizes;
   * the choice is invariant under a power-of-two scaling of the gradient (argmax of -(g*(y-yhat))^2);

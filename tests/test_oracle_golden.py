@@ -53,3 +53,24 @@ def test_nonbatching_class_agrees_on_config1_golden():
     z, _ = C.load_golden("config1")
     assert np.array_equal(z["w_interval"], z["nonbatching_w_interval"])
     assert np.array_equal(z["a_interval"], z["nonbatching_a_interval"])
+
+
+def test_conv_oracle_matches_reference():
+    """oracle.conv_calibrate vs the golden made by the reference's ChannelwiseBatchingQuantConv2d (a_bit = 32) on the CPU."""
+    import os
+    z = np.load(os.path.join(C.GOLD, "conv_small.npz"))
+    x, W, b, y, g = O.make_conv_fixture(31, 4, 3, 32, 16, 4)
+    w_int, scores = O.conv_calibrate(W, b, x, y, g, stride=4)
+    C.assert_scores_close(scores.numpy(), z["scores_000"], 2e-5, "conv_small")
+    assert C.rel_err(w_int.numpy(), z["w_interval"]) < 1e-6
+
+
+def test_calibrator_golden_is_complete():
+    """tests/golden/calib_tiny_vit.npz (reference HessianQuantCalibrator on the tiny ViT): every module, both modes."""
+    import os
+    z = np.load(os.path.join(C.GOLD, "calib_tiny_vit.npz"))
+    names = {k.split("|")[1] for k in z.files}
+    assert len(names) == 14 and "patch_embed.proj" in names and "head" in names
+    assert {k.split("|")[0] for k in z.files} == {"par", "seq"}
+    # sequential mode: the reference's matmul1 sees zero gradients behind the quantized proj and picks candidate 0
+    assert float(z["seq|blocks.0.attn.matmul1|A_interval"].max()) < 0.05 * float(z["par|blocks.0.attn.matmul1|A_interval"].min())
