@@ -82,11 +82,21 @@ def _cat_captured(module):
 
 
 # ---------------------------------------------------------------- work model + sharding
+# Measured on a B200 (profiles/README.md, round 2; ViT-B/224 x 32 images, one search round): qkv 11.4 ms, proj 5.9 ms,
+# fc1 14.3 ms, fc2 16.7 ms, head 2.7 ms, matmul1 6.0 ms, matmul2 5.0 ms, patch-embedding conv 5.1 ms (once).  A fixed
+# part per module and round (operand images, per-step launches) plus executed work at the rate each kernel family sustains.
+_ROUND_OVERHEAD_S = 2.5e-3
+_LINEAR_RATE = 4.2e14      # "units" below per second: eq_n * 2*M*K*O * (1 + n_a)
+_MATMUL_RATE = 1.1e14      # 2 * eq_n * 2*b*H*S1*S2*S3 per second (197-token tiles are 59 % full)
+_CONV_RATE = 1.5e13        # eq_n * 2 * MACs per second (three bf16 term products per MAC)
+
+
 def module_cost(module, n_img, shapes=None, tokens_hint=197):
-    """Relative cost of one module's search (executed work of the CUDA path, not full-GEMM units):
-    Linear  : rounds * eq_n * 2*M*K*O * (1 [all weight steps together: each multiplies one K slab] + n_a [activation steps])
-    MatMul  : rounds * 2 * eq_n * 2*b*H*S1*S2*S3
-    `shapes` = per-image input shapes recorded by a probe forward ({"x": (tokens.., K)} / {"A": (H,S1,S2), "B": (H,S2,S3)})."""
+    """Estimated seconds of one module's search on a B200 (only ratios matter for the sharding).
+    Linear  : rounds * (overhead + eq_n * 2*M*K*O * (1 [all weight steps together multiply each K slab once] + n_a) / rate)
+    MatMul  : rounds * (overhead + 2 * eq_n * 2*b*H*S1*S2*S3 / rate)
+    `shapes` = per-image input shapes recorded by a probe forward ({"x": (lead, tokens.., K)} / {"A": (lead, H, S1, S2), ...});
+    `lead` folds windows into the batch (Swin)."""
     rounds = getattr(module, "search_round", 1)
     eq_n = getattr(module, "eq_n", 1)
     if isinstance(module, MinMaxQuantLinear):
@@ -96,9 +106,10 @@ def module_cost(module, n_img, shapes=None, tokens_hint=197):
             for s in shapes["x"][:-1]:
                 rows *= int(s)
         gemm = 2.0 * n_img * rows * module.in_features * module.out_features
-        return float(rounds * eq_n) * gemm * (1.0 + getattr(module, "n_a", 1))
+        return rounds * (_ROUND_OVERHEAD_S + eq_n * gemm * (1.0 + getattr(module, "n_a", 1)) / _LINEAR_RATE)
     if isinstance(module, MinMaxQuantConv2d):
-        return 0.0 if shapes is None else float(rounds * eq_n) * 2.0 * n_img * shapes.get("conv_macs", 0.0)
+        macs = 0.0 if shapes is None else shapes.get("conv_macs", 0.0)
+        return _ROUND_OVERHEAD_S + eq_n * 2.0 * n_img * macs / _CONV_RATE          # searched once (see quant_layers/conv.py)
     if isinstance(module, MinMaxQuantMatMul):
         if shapes is not None and "A" in shapes:
             H, S1, S2 = [int(s) for s in shapes["A"][-3:]]
@@ -108,7 +119,7 @@ def module_cost(module, n_img, shapes=None, tokens_hint=197):
                 lead *= int(s)
         else:
             lead, H, S1, S2, S3 = 1, 12, tokens_hint, 64, tokens_hint
-        return float(rounds * 2 * eq_n) * 2.0 * n_img * lead * H * S1 * S2 * S3
+        return rounds * (_ROUND_OVERHEAD_S + 2 * eq_n * 2.0 * n_img * lead * H * S1 * S2 * S3 / _MATMUL_RATE)
     return 0.0
 
 
