@@ -265,12 +265,16 @@ __global__ void __launch_bounds__(1024) select_step_kernel(const SelectArgs a) {
   const double gs = (double)a.gscale[0];
   const double norm = a.inv_count / (gs * gs);
   for (int g = warp; g < a.n_groups; g += nwarps) {
-    double bv = 0.0; int bi = -1;
+    // The comparison runs on the fp32-rounded score, like the reference's argmax over its fp32 similarity tensor
+    // (linear.py:493, :531): candidates whose scores round to the same float tie, and the first one wins.  (Comparing
+    // the fp64 sums would pick the later candidate of such a pair and send that row block down another greedy path;
+    // it would also disagree with the argmax of the logged fp32 table.)
+    float bv = 0.f; int bi = -1;
     for (int c = lane; c < a.n_cand; c += 32) {      // ascending c: strict '>' keeps the first maximum
       double sacc = 0.0;
       for (int k = 0; k < a.keys_per_group; ++k) sacc += a.sums[(size_t)c * a.n_keys + g * a.keys_per_group + k];
-      const double v = -sacc * norm;
-      if (a.score_log) a.score_log[(size_t)c * a.n_groups + g] = (float)v;
+      const float v = (float)(-sacc * norm);
+      if (a.score_log) a.score_log[(size_t)c * a.n_groups + g] = v;
       bool take;
       if (bi < 0) take = true;
       else if (bv != bv) take = false;               // an earlier NaN already won
@@ -278,7 +282,7 @@ __global__ void __launch_bounds__(1024) select_step_kernel(const SelectArgs a) {
       if (take) { bv = v; bi = c; }
     }
     for (int o = 16; o > 0; o >>= 1) {
-      const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
       const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
       bool take;
       if (oi < 0) take = false;
