@@ -152,11 +152,19 @@ class PTQSLQuantMatMul(MinMaxQuantMatMul):
         self.keep_scores = False
         self.last_scores = None
 
+    _force_headwise = False       # the Batching classes set n_G = heads (matmul.py:411-417)
+
     def _get_padding_parameters(self, A, B):
-        """reference: matmul.py:109-122 with the head-wise override :411-417"""
-        self.n_G_A = A.shape[1]
-        self.n_G_B = B.shape[1]
-        self.crb_groups_A = self.crb_groups_B = 1
+        """reference: matmul.py:109-122 (groups of consecutive heads, zero padding).  The B200 path implements the two
+        layouts PTQ4ViT meets: one group per head (what the Batching classes force, :411-417) and one group for all
+        heads (the constructor default n_G = 1 of the non-batching classes)."""
+        H = A.shape[1]
+        if self._force_headwise:
+            self.n_G_A = self.n_G_B = H
+        for n_G in (self.n_G_A, self.n_G_B):
+            if n_G not in (1, H):
+                raise NotImplementedError(f"ptq4vit_b200 MatMul search: n_G must be 1 or the number of heads ({H}), got {n_G}")
+        self.crb_groups_A, self.crb_groups_B = H // self.n_G_A, H // self.n_G_B
         self.crb_rows_A, self.crb_cols_A = A.shape[2], A.shape[3]
         self.crb_rows_B, self.crb_cols_B = B.shape[2], B.shape[3]
         self.pad_groups_A = self.pad_groups_B = 0
@@ -178,6 +186,11 @@ class PTQSLQuantMatMul(MinMaxQuantMatMul):
         A_, B_, Y_, G_ = self._cuda(A), self._cuda(B), self._cuda(Y), self._cuda(G)
         dev = A_.device
         self._get_padding_parameters(A_, B_)
+        n_G = self.n_G_B if self.sos else self.n_G_A
+        if not self.sos and self.n_G_A != self.n_G_B:
+            raise NotImplementedError("ptq4vit_b200 MatMul search: A and B must use the same group layout")
+        if n_G == 1 and A_.shape[1] > 1:      # one group for all heads: the heads become part of the batch
+            A_, B_, Y_, G_ = [t.reshape(-1, 1, t.shape[2], t.shape[3]) for t in (A_, B_, Y_, G_)]
         d = self._desc(A_, B_, self.search_round, (self.eq_alpha, self.eq_beta, self.eq_n))
         H = d.heads
         lib = _lib.lib()
@@ -231,6 +244,7 @@ class SoSPTQSLQuantMatMul(PTQSLQuantMatMul):
 
 class PTQSLBatchingQuantMatMul(PTQSLQuantMatMul):
     """reference: quant_layers/matmul.py:390-576"""
+    _force_headwise = True
 
     def _initialize_calib_parameters(self):
         """reference: matmul.py:396-409; a whole layer fits in HBM, no batching."""

@@ -207,3 +207,48 @@ def test_base_batching_quant_calib_l2():
     torch.cuda.synchronize()
     assert all(m.calibrated for m in wrapped.values())
     importlib.reload(cfg)
+
+
+def test_hessian_quant_calib_non_batching_driver_matches_reference():
+    """HessianQuantCalibrator.quant_calib (reference :216-298): the non-batching driver -- per module one forward+backward
+    sweep, then `calibration_step2(x)` / `(A, B)` of the NON-batching classes with the hessian metric -- against the
+    reference's same driver on its own non-batching classes (Linear and MatMul modules; both nets wrapped by hand)."""
+    if not RH.available():
+        pytest.skip("needs the staged reference (baseline/_ref)")
+    import copy
+    from ptq4vit_b200.quant_layers import linear as L, matmul as M
+    from ptq4vit_b200.utils import quant_calib as Q
+    from ptq4vit_b200.utils.models import MatMul
+    R = RH.load()
+    kw = dict(metric="hessian", eq_alpha=0.01, eq_beta=1.2, eq_n=100, search_round=2)
+
+    def wrap(net, lin, gelu, mm, sos, matmul_type):
+        wrapped = {}
+        for name, m in list(net.named_modules()):
+            parent = net.get_submodule(name.rsplit(".", 1)[0]) if "." in name else net
+            leaf = name.rsplit(".", 1)[-1]
+            if isinstance(m, torch.nn.Linear):
+                q = (gelu if leaf == "fc2" else lin)(m.in_features, m.out_features, n_V=3 if leaf == "qkv" else 1, **kw)
+                q.weight.data = m.weight.data; q.bias = m.bias; q.to(m.weight.device)
+            elif isinstance(m, matmul_type):
+                q = (sos if leaf == "matmul2" else mm)(**kw)
+            else:
+                continue
+            setattr(parent, leaf, q); wrapped[name] = q
+        return wrapped
+
+    net = _net()
+    net_r = copy.deepcopy(net)
+    for mod in net_r.modules():
+        for leaf in ("matmul1", "matmul2"):
+            if hasattr(mod, leaf):
+                setattr(mod, leaf, R.models.MatMul())
+    ours = wrap(net, L.PTQSLQuantLinear, L.PostGeluPTQSLQuantLinear, M.PTQSLQuantMatMul, M.SoSPTQSLQuantMatMul, MatMul)
+    refs = wrap(net_r, R.linear.PTQSLQuantLinear, R.linear.PostGeluPTQSLQuantLinear, R.matmul.PTQSLQuantMatMul,
+                R.matmul.SoSPTQSLQuantMatMul, R.models.MatMul)
+    Q.HessianQuantCalibrator(net, ours, RH.ListLoader(RH.tiny_images()), sequential=False, batch_size=4).quant_calib()
+    R.quant_calib.HessianQuantCalibrator(net_r, refs, RH.ListLoader(RH.tiny_images()), sequential=False, batch_size=4).quant_calib()
+    torch.cuda.synchronize()
+    assert all(m.calibrated and m.mode == "quant_forward" for m in ours.values())
+    bad, n = _count_diff(RH.collect_intervals(ours), RH.collect_intervals(refs), "non-batching hessian driver", max_frac=0.1)
+    print(f"[calibrator non-batching] {len(ours)} modules, {bad}/{n} step sizes differ")
