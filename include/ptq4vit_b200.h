@@ -48,6 +48,7 @@ typedef struct p4v_linear_desc {
   int32_t has_bias;
   int32_t operand;   /* P4V_OPERAND_*  */
   int32_t kernel;    /* P4V_KERNEL_*   */
+  int32_t init_layerwise; /* 1: every block starts from the layer-wise min-max step size (linear.py:382-383, :393-394) */
 } p4v_linear_desc;
 
 /* bytes of device workspace p4v_linear_* needs for this layer */
@@ -100,6 +101,7 @@ typedef struct p4v_matmul_desc {
   int32_t sos;       /* 1: split-of-softmax twin-uniform A (matmul.py:578-644)  */
   int32_t operand;
   int32_t kernel;
+  int32_t init_layerwise; /* 1: every head starts from the layer-wise min-max step size (matmul.py:430-432) */
 } p4v_matmul_desc;
 
 P4V_API int p4v_matmul_workspace_bytes(const p4v_matmul_desc* d, size_t* bytes);

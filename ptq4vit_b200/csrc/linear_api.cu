@@ -589,6 +589,10 @@ int begin_impl(const LinPlan& p, const float* x, const float* W, const float* g,
   if ((rc = p4v_block_max(W, p.K, p.O, p.crb_rows, p.d.n_V, p.crb_cols, p.d.n_H, 1, keys, st))) return rc;
   if ((rc = p4v_block_max(x, p.K, p.M, p.M, 1, p.crb_acts, p.d.n_a, p.twin ? 0 : 1, keys + nW, st))) return rc;
   if ((rc = p4v_block_max(g, p.O, p.M, p.M, 1, p.O, 1, 1, keys + nW + p.d.n_a, st))) return rc;
+  if (p.d.init_layerwise) {       // linear.py:382-383, :393-394: one step size for the whole weight / activation tensor
+    if ((rc = p4v_keys_broadcast_max(keys, nW, st))) return rc;
+    if ((rc = p4v_keys_broadcast_max(keys + nW, p.d.n_a, st))) return rc;
+  }
   if ((rc = p4v_keys_to_delta(keys, nW, (float)p.w_qmax - 0.5f, at<float>(ws, p.o_dW0), at<float>(ws, p.o_dW), st))) return rc;
   if ((rc = p4v_keys_to_delta(keys + nW, p.d.n_a, (float)p.a_qmax - 0.5f, at<float>(ws, p.o_dX0), at<float>(ws, p.o_dX), st))) return rc;
   if ((rc = p4v_make_gscale(keys + nW + p.d.n_a, at<float>(ws, p.o_gscale), st))) return rc;

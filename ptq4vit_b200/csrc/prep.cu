@@ -84,6 +84,18 @@ __global__ void keys_to_delta_kernel(const int* keys, int n, float denom, int ie
   }
 }
 
+// init_layerwise: every key of the range becomes the maximum of the range (one block)
+__global__ void keys_broadcast_max_kernel(int* keys, int n) {
+  __shared__ int m;
+  if (threadIdx.x == 0) m = kKeyMin;
+  __syncthreads();
+  int v = kKeyMin;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) v = max(v, keys[i]);
+  atomicMax(&m, v);
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) keys[i] = m;
+}
+
 __global__ void make_gscale_kernel(const int* key, float* gscale) {
   float m = key2f(key[0]);
   float s = 1.f;
@@ -364,6 +376,11 @@ int p4v_group_absmax(const float* src, long long prob_elems, int P, int n_groups
   return 0;
 }
 
+int p4v_keys_broadcast_max(int* keys, int n, cudaStream_t st) {
+  keys_broadcast_max_kernel<<<1, 256, 0, st>>>(keys, n); p4v_count_launch();
+  P4V_CUDA_OK(cudaGetLastError());
+  return 0;
+}
 int p4v_scalar_div_ieee() {
   const char* e = getenv("P4V_SCALAR_DIV");      // "ieee": reference executed on the CPU; default: reference executed on the GPU
   return (e && e[0] == 'i') ? 1 : 0;

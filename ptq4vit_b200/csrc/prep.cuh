@@ -41,6 +41,7 @@ int p4v_block_max(const float* src, long long ld, int rows, int row_block, int n
 int p4v_group_absmax(const float* src, long long prob_elems, int P, int n_groups, int* keys, cudaStream_t st);
 int p4v_keys_reset(int* keys, int n, cudaStream_t st);
 // delta[i] = key_to_float(keys[i]) / denom ; optionally copy to a second array
+int p4v_keys_broadcast_max(int* keys, int n, cudaStream_t st);     // init_layerwise: all keys of the range := their maximum
 int p4v_scalar_div_ieee();
 int p4v_keys_to_delta(const int* keys, int n, float denom, float* d0, float* d1, cudaStream_t st);
 // gscale = 2^-floor(log2(max|g|)) (1 if max is 0 / non-finite)

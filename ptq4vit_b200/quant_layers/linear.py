@@ -90,6 +90,7 @@ class MinMaxQuantLinear(nn.Linear):
         d.has_bias = 0 if self.bias is None else 1
         d.operand = _lib.default_operand()
         d.kernel = _lib.default_kernel()
+        d.init_layerwise = 1 if getattr(self, "init_layerwise", False) else 0
         return d
 
     def _device(self):
@@ -213,8 +214,6 @@ class PTQSLQuantLinear(MinMaxQuantLinear):
         raise NotImplementedError(f"metric {self.metric} not implemented!")
 
     def _native_calibrate(self, x, y, g):
-        if self.init_layerwise:
-            raise NotImplementedError("init_layerwise=True is not supported by the B200 search path")
         dev = self._device()
         tokens = 1
         if x.dim() > 2:

@@ -88,6 +88,7 @@ class MinMaxQuantMatMul(nn.Module):
         d.sos = 1 if self.sos else 0
         d.operand = _lib.default_operand()
         d.kernel = _lib.default_kernel()
+        d.init_layerwise = 1 if getattr(self, "init_layerwise", False) else 0
         return d
 
     @staticmethod
@@ -181,8 +182,6 @@ class PTQSLQuantMatMul(MinMaxQuantMatMul):
     def _native_calibrate(self, A, B, Y, G):
         if (self.n_V_A, self.n_H_A, self.n_V_B, self.n_H_B) != (1, 1, 1, 1):
             raise NotImplementedError("ptq4vit_b200 MatMul search implements the head-wise layout only (n_V = n_H = 1)")
-        if self.init_layerwise:
-            raise NotImplementedError("init_layerwise=True is not supported by the B200 search path")
         A_, B_, Y_, G_ = self._cuda(A), self._cuda(B), self._cuda(Y), self._cuda(G)
         dev = A_.device
         self._get_padding_parameters(A_, B_)

@@ -211,3 +211,32 @@ def test_vitb_matmul_matches_reference_on_gpu(sos, bit):
     _write_report()
     print(f"[reference parity] {name} W{bit} ({kind}): flips {flips}/{compared}, worst score err {worst:.2e}, "
           f"dA {a_err:.1e} dB {b_err:.1e} out {o_err:.1e}; reference {ref_s:.2f}s vs ours {our_s * 1e3:.1f} ms")
+
+
+def test_init_layerwise_matches_reference_on_gpu():
+    """init_layerwise=True (linear.py:382-383, :393-394; matmul.py:430-432): every block / head starts from the
+    layer-wise min-max step size, so the candidate grid itself changes."""
+    if not RH.available():
+        pytest.skip("needs the staged reference (baseline/_ref)")
+    from ptq4vit_b200.quant_layers.linear import PTQSLBatchingQuantLinear
+    from ptq4vit_b200.quant_layers.matmul import PTQSLBatchingQuantMatMul
+    x, W, b, y, g = O.make_linear_fixture(301, 8, 50, 128, 192)
+    mod = dict(n_V=3, n_H=4, n_a=2, w_bit=8, a_bit=8, search_round=2, init_layerwise=True)
+    ref = RH.run_linear(x, W, b, y, g, quant_forward=False, **mod)
+    m = PTQSLBatchingQuantLinear(128, 192, metric="hessian", eq_alpha=0.01, eq_beta=1.2, eq_n=100, **mod)
+    m.weight.data = W.clone(); m.bias.data = b.clone(); m.cuda(); m.keep_scores = True
+    m.raw_input, m.raw_out, m.raw_grad = x.cuda(), y.cuda(), g.cuda()
+    with torch.no_grad():
+        m.calibration_step2()
+    flips, worst, _ = _compare_steps("init_layerwise linear", [s.cpu().numpy() for s in m.last_scores], [s.numpy() for s in ref["scores"]], 0)
+    assert flips == 0 and worst < 1e-5
+    assert float((m.w_interval.cpu().reshape(-1) - ref["w_interval"].reshape(-1)).abs().max()) == 0.0
+    assert float((m.a_interval.cpu().reshape(-1) - ref["a_interval"].reshape(-1)).abs().max()) == 0.0
+    A, B, Y, G = O.make_matmul_fixture(302, 4, 3, 50, 32, 50)
+    refm = RH.run_matmul(A, B, Y, G, quant_forward=False, search_round=2, init_layerwise=True)
+    mm = PTQSLBatchingQuantMatMul(metric="hessian", eq_alpha=0.01, eq_beta=1.2, eq_n=100, search_round=2, init_layerwise=True)
+    mm.raw_input, mm.raw_out, mm.raw_grad = [A.cuda(), B.cuda()], Y.cuda(), G.cuda()
+    with torch.no_grad():
+        mm.calibration_step2()
+    assert float((mm.A_interval.cpu().reshape(-1) - refm["A_interval"].reshape(-1)).abs().max()) == 0.0
+    assert float((mm.B_interval.cpu().reshape(-1) - refm["B_interval"].reshape(-1)).abs().max()) == 0.0
