@@ -13,6 +13,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import _lib
+from ._metric import metric_weight
 
 
 class MinMaxQuantConv2d(nn.Conv2d):
@@ -129,12 +130,8 @@ class ChannelwiseBatchingQuantConv2d(PTQSLQuantConv2d):
         self.calib_batch_size = int(self.raw_input.shape[0])
 
     def _grad_for_metric(self, y):
-        if self.metric == "hessian":
-            assert self.raw_grad is not None, "raw_grad is None in _get_similarity!"     # conv.py:518
-            return self.raw_grad
-        if self.metric == "L2_norm":
-            return torch.ones_like(y)
-        raise NotImplementedError(f"metric {self.metric} not implemented!")
+        """Per-element weight of the metric (conv.py:509-522); see _metric.py."""
+        return metric_weight(self.metric, y, self.raw_grad, "_get_similarity")
 
     def calibration_step2(self):
         """reference: conv.py:591-603.  The weight search does not depend on anything the rounds change when the

@@ -12,6 +12,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .. import _lib
+from ._metric import metric_weight
 
 GELU_MIN_NEG = 0.16997124254703522  # reference: quant_layers/linear.py:574
 
@@ -206,12 +207,8 @@ class PTQSLQuantLinear(MinMaxQuantLinear):
 
     # ---- native search ---------------------------------------------------
     def _grad_for_metric(self, y):
-        if self.metric == "hessian":
-            assert self.raw_grad is not None, "raw_grad is None in _get_similarity!"   # linear.py:418
-            return self.raw_grad
-        if self.metric == "L2_norm":
-            return torch.ones_like(y)       # -(y-yhat)^2 == hessian metric with unit gradient (linear.py:411-412)
-        raise NotImplementedError(f"metric {self.metric} not implemented!")
+        """Per-element weight of the metric (linear.py:406-422); see _metric.py."""
+        return metric_weight(self.metric, y, self.raw_grad, "_get_similarity")
 
     def _native_calibrate(self, x, y, g):
         dev = self._device()

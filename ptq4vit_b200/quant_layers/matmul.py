@@ -10,6 +10,7 @@ import torch
 from torch import nn
 
 from .. import _lib
+from ._metric import metric_weight
 
 
 class _QuantMatMulFn(torch.autograd.Function):
@@ -172,12 +173,8 @@ class PTQSLQuantMatMul(MinMaxQuantMatMul):
         self.pad_rows_A = self.pad_rows_B = self.pad_cols_A = self.pad_cols_B = 0
 
     def _grad_for_metric(self, y):
-        if self.metric == "hessian":
-            assert self.raw_grad is not None, "No raw_grad in PTQSLBatchingQuantMatMul!"     # matmul.py:475
-            return self.raw_grad
-        if self.metric == "L2_norm":
-            return torch.ones_like(y)
-        raise NotImplementedError(f"metric {self.metric} not implemented!")
+        """Per-element weight of the metric (matmul.py:465-479); see _metric.py."""
+        return metric_weight(self.metric, y, self.raw_grad, "PTQSLBatchingQuantMatMul")
 
     def _native_calibrate(self, A, B, Y, G):
         if (self.n_V_A, self.n_H_A, self.n_V_B, self.n_H_B) != (1, 1, 1, 1):

@@ -242,3 +242,50 @@ def test_init_layerwise_matches_reference_on_gpu():
     ra = (mm.A_interval.cpu().reshape(-1) - refm["A_interval"].reshape(-1)).abs() / refm["A_interval"].reshape(-1)
     rb = (mm.B_interval.cpu().reshape(-1) - refm["B_interval"].reshape(-1)).abs() / refm["B_interval"].reshape(-1)
     assert int((ra > 2e-6).sum()) + int((rb > 2e-6).sum()) <= 1 and float(torch.cat([ra, rb]).max()) < 0.05
+
+
+@pytest.mark.parametrize("metric", ["L2_norm", "linear_weighted_L2_norm", "square_weighted_L2_norm"])
+def test_squared_error_metrics_match_reference_on_gpu(metric):
+    """The reference's other squared-error metrics (linear.py:411-416, matmul.py:467-472, conv.py:511-516) through the
+    same kernels, against the unmodified reference running that metric itself."""
+    if not RH.available():
+        pytest.skip("needs the staged reference (baseline/_ref)")
+    from ptq4vit_b200.quant_layers.conv import ChannelwiseBatchingQuantConv2d
+    from ptq4vit_b200.quant_layers.linear import PTQSLBatchingQuantLinear
+    from ptq4vit_b200.quant_layers.matmul import PTQSLBatchingQuantMatMul
+    x, W, b, y, g = O.make_linear_fixture(401, 8, 50, 128, 192)
+    mod = dict(n_V=3, n_H=4, n_a=2, w_bit=8, a_bit=8, search_round=2, metric=metric)
+    ref = RH.run_linear(x, W, b, y, g, quant_forward=False, **mod)
+    m = PTQSLBatchingQuantLinear(128, 192, eq_alpha=0.01, eq_beta=1.2, eq_n=100, **mod)
+    m.weight.data = W.clone(); m.bias.data = b.clone(); m.cuda(); m.keep_scores = True
+    m.raw_input, m.raw_out, m.raw_grad = x.cuda(), y.cuda(), None
+    with torch.no_grad():
+        m.calibration_step2()
+    flips, worst, _ = _compare_steps(f"{metric} linear", [s.cpu().numpy() for s in m.last_scores], [s.numpy() for s in ref["scores"]], 0)
+    assert worst < 1e-5 and flips <= 1
+    if flips == 0:
+        assert float((m.w_interval.cpu().reshape(-1) - ref["w_interval"].reshape(-1)).abs().max()) == 0.0
+        assert float((m.a_interval.cpu().reshape(-1) - ref["a_interval"].reshape(-1)).abs().max()) == 0.0
+    A, B, Y, G = O.make_matmul_fixture(402, 4, 3, 50, 32, 50)
+    refm = RH.run_matmul(A, B, Y, G, quant_forward=False, search_round=1, metric=metric)
+    mm = PTQSLBatchingQuantMatMul(metric=metric, eq_alpha=0.01, eq_beta=1.2, eq_n=100, search_round=1)
+    mm.keep_scores = True
+    mm.raw_input, mm.raw_out, mm.raw_grad = [A.cuda(), B.cuda()], Y.cuda(), None
+    with torch.no_grad():
+        mm.calibration_step2()
+    fl, worst_m, _ = _compare_steps(f"{metric} matmul", [s.cpu().numpy() for s in mm.last_scores], [s.numpy() for s in refm["scores"]], 1)
+    assert worst_m < 1e-5 and fl <= 1
+    if fl == 0:
+        assert float((mm.A_interval.cpu().reshape(-1) - refm["A_interval"].reshape(-1)).abs().max()) == 0.0
+        assert float((mm.B_interval.cpu().reshape(-1) - refm["B_interval"].reshape(-1)).abs().max()) == 0.0
+    xc, Wc, bc, yc, gc = O.make_conv_fixture(403, 4, 3, 32, 16, 4)
+    refc = RH.run_conv(xc, Wc, bc, yc, gc, stride=4, metric=metric)
+    cv = ChannelwiseBatchingQuantConv2d(3, 32, (4, 4), stride=4, a_bit=32, metric=metric, eq_alpha=0.01, eq_beta=1.2, eq_n=100)
+    cv.weight.data = Wc.clone(); cv.bias.data = bc.clone(); cv.cuda(); cv.keep_scores = True
+    cv.raw_input, cv.raw_out, cv.raw_grad = xc.cuda(), yc.cuda(), None
+    with torch.no_grad():
+        cv.calibration_step2()
+    rs = refc["scores"][0].reshape(100, -1).double(); gs = cv.last_scores[0].cpu().double()
+    assert float((gs - rs).abs().max() / rs.abs().max()) < SCORE_RTOL
+    differing = int((cv.w_interval.cpu().reshape(-1) != refc["w_interval"].reshape(-1)).sum())
+    assert differing <= 1, f"{metric} conv: {differing} channels differ"

@@ -78,3 +78,37 @@ def test_module_cost_uses_probed_shapes():
     qk = M.PTQSLBatchingQuantMatMul(search_round=1)
     assert abs(Q.module_cost(qkv, 32, {"x": (1, 197, 768)}) / 11.4e-3 - 1) < 0.2
     assert abs(Q.module_cost(qk, 32, {"A": (1, 12, 197, 64), "B": (1, 12, 64, 197)}) / 6.0e-3 - 1) < 0.2
+
+
+@needs_ref
+@pytest.mark.parametrize("metric", ["L2_norm", "linear_weighted_L2_norm", "square_weighted_L2_norm"])
+def test_weighted_l2_metrics_are_hessian_with_a_surrogate_weight(metric):
+    """The product evaluates the reference's squared-error metrics (linear.py:411-416, matmul.py:467-472,
+    conv.py:511-516) as the Hessian metric with a surrogate per-element weight (quant_layers/_metric.py).  The
+    reference itself must pick the same candidates either way."""
+    from ptq4vit_b200.quant_layers._metric import metric_weight
+    x, W, b, y, g = O.make_linear_fixture(41, 4, 20, 32, 48)
+    mod = dict(n_V=3, n_H=2, n_a=2, search_round=2, eq_n=25)
+    direct = RH.run_linear(x, W, b, y, g, quant_forward=False, metric=metric, **mod)
+    via = RH.run_linear(x, W, b, y, metric_weight(metric, y, None, "test").clone(), quant_forward=False, metric="hessian", **mod)
+    assert torch.equal(direct["w_interval"], via["w_interval"]) and torch.equal(direct["a_interval"], via["a_interval"])
+    for sd, sv in zip(direct["scores"], via["scores"]):
+        assert float((sd - sv).abs().max() / sd.abs().max()) < 1e-5
+    A, B, Y, G = O.make_matmul_fixture(42, 2, 3, 12, 8, 12)
+    dm = RH.run_matmul(A, B, Y, G, quant_forward=False, metric=metric, search_round=1, eq_n=25)
+    vm = RH.run_matmul(A, B, Y, metric_weight(metric, Y, None, "test").clone(), quant_forward=False, metric="hessian", search_round=1, eq_n=25)
+    assert torch.equal(dm["A_interval"], vm["A_interval"]) and torch.equal(dm["B_interval"], vm["B_interval"])
+    xc, Wc, bc, yc, gc = O.make_conv_fixture(43, 2, 3, 8, 8, 4)
+    dc = RH.run_conv(xc, Wc, bc, yc, gc, stride=4, metric=metric, eq_n=25)
+    vc = RH.run_conv(xc, Wc, bc, yc, metric_weight(metric, yc, None, "test").clone(), stride=4, metric="hessian", eq_n=25)
+    assert torch.equal(dc["w_interval"], vc["w_interval"])
+
+
+def test_unsupported_metrics_raise_like_the_reference():
+    from ptq4vit_b200.quant_layers._metric import metric_weight
+    y = torch.ones(2, 3)
+    for metric in ("cosine", "L1_norm", "pearson", "nonsense"):
+        with pytest.raises(NotImplementedError):
+            metric_weight(metric, y, None, "test")
+    with pytest.raises(AssertionError):
+        metric_weight("hessian", y, None, "test")
