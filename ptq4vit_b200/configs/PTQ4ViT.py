@@ -22,28 +22,34 @@ ptqsl_matmul_kwargs = {"metric": "hessian", "eq_alpha": 0.01, "eq_beta": 1.2, "e
                        "n_G_A": 1, "n_V_A": 1, "n_H_A": 1, "n_G_B": 1, "n_V_B": 1, "n_H_B": 1}
 
 
+def _linear_class(module_type):
+    if module_type == "qlinear_MLP_2" and not no_postgelu:
+        return PostGeluPTQSLBatchingQuantLinear          # twin-uniform post-GELU input (configs/PTQ4ViT.py:61-65)
+    return PTQSLBatchingQuantLinear
+
+
+def _matmul_class(module_type):
+    if module_type == "qmatmul_scorev" and not no_softmax:
+        return SoSPTQSLBatchingQuantMatMul               # split-of-softmax A operand (configs/PTQ4ViT.py:75-79)
+    return PTQSLBatchingQuantMatMul
+
+
+# per-type edits of the shared Linear kwargs: q, k and v each get their own row blocks; the classifier head keeps one
+_N_V_RULE = {"qlinear_qkv": lambda n_V: 3 * n_V, "qlinear_classifier": lambda n_V: 1}
+
+
 def get_module(module_type, *args, **kwargs):
+    """reference: configs/PTQ4ViT.py:51-80.  The kwargs dicts and the two switches are read at call time, so an
+    experiment's cfg_modifier can edit them between calls (example/test_all.py:59-75)."""
     if module_type == "qconv":
-        kwargs.update(ptqsl_conv2d_kwargs)
-        module = ChannelwiseBatchingQuantConv2d(*args, **kwargs, w_bit=w_bit["qconv"], a_bit=32)  # activation quantization off
-    elif "qlinear" in module_type:
-        kwargs.update(ptqsl_linear_kwargs)
-        if module_type == "qlinear_qkv":
-            kwargs["n_V"] *= 3  # q, k, v
-            module = PTQSLBatchingQuantLinear(*args, **kwargs, w_bit=w_bit[module_type], a_bit=a_bit[module_type])
-        elif module_type == "qlinear_MLP_2":
-            cls = PTQSLBatchingQuantLinear if no_postgelu else PostGeluPTQSLBatchingQuantLinear
-            module = cls(*args, **kwargs, w_bit=w_bit[module_type], a_bit=a_bit[module_type])
-        elif module_type == "qlinear_classifier":
-            kwargs["n_V"] = 1
-            module = PTQSLBatchingQuantLinear(*args, **kwargs, w_bit=w_bit[module_type], a_bit=a_bit[module_type])
-        else:
-            module = PTQSLBatchingQuantLinear(*args, **kwargs, w_bit=w_bit[module_type], a_bit=a_bit[module_type])
-    elif "qmatmul" in module_type:
-        kwargs.update(ptqsl_matmul_kwargs)
-        if module_type == "qmatmul_qk":
-            module = PTQSLBatchingQuantMatMul(*args, **kwargs, A_bit=A_bit[module_type], B_bit=B_bit[module_type])
-        elif module_type == "qmatmul_scorev":
-            cls = PTQSLBatchingQuantMatMul if no_softmax else SoSPTQSLBatchingQuantMatMul
-            module = cls(*args, **kwargs, A_bit=A_bit[module_type], B_bit=B_bit[module_type])
-    return module
+        opts = {**kwargs, **ptqsl_conv2d_kwargs}
+        return ChannelwiseBatchingQuantConv2d(*args, **opts, w_bit=w_bit["qconv"], a_bit=32)   # activation quantizer off
+    if "qlinear" in module_type:
+        opts = {**kwargs, **ptqsl_linear_kwargs}
+        if module_type in _N_V_RULE:
+            opts["n_V"] = _N_V_RULE[module_type](opts["n_V"])
+        return _linear_class(module_type)(*args, **opts, w_bit=w_bit[module_type], a_bit=a_bit[module_type])
+    if "qmatmul" in module_type:
+        opts = {**kwargs, **ptqsl_matmul_kwargs}
+        return _matmul_class(module_type)(*args, **opts, A_bit=A_bit[module_type], B_bit=B_bit[module_type])
+    raise NotImplementedError(f"unknown module type {module_type}")
